@@ -1,0 +1,131 @@
+// Library-internal plumbing shared by the .cu translation units: the context object behind
+// `b2s_ctx` (include/b200snark.h), error handling that never unwinds across the C ABI, stream-ordered
+// device buffers and the kernel-launch counter that bench.py reports as `gpu_launches`.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/b200snark.h"
+#include "curves.cuh"
+
+namespace b2s {
+
+struct NttPlan;  // ntt.cu
+
+struct Ctx {
+    int curve = 0;
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    std::mutex mu;
+    std::string err;
+    uint64_t launches = 0;
+    int sm_count = 148;
+    std::map<uint32_t, NttPlan*> ntt_plans;   // keyed by log_n
+    void* fixed_base_tables[2] = {nullptr, nullptr};  // G1 / G2 window tables (setup.cu)
+};
+
+inline int32_t fail(Ctx* c, int32_t code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    if (c) c->err = buf;
+    return code;
+}
+
+#define B2S_CUDA(ctx, expr)                                                                         \
+    do {                                                                                            \
+        cudaError_t e__ = (expr);                                                                   \
+        if (e__ != cudaSuccess)                                                                     \
+            return ::b2s::fail(ctx, e__ == cudaErrorMemoryAllocation ? B2S_ERR_OOM : B2S_ERR_CUDA, \
+                               "%s:%d %s: %s", __FILE__, __LINE__, #expr, cudaGetErrorString(e__)); \
+    } while (0)
+
+#define B2S_TRY(expr)                 \
+    do {                              \
+        int32_t s__ = (expr);         \
+        if (s__ != B2S_OK) return s__; \
+    } while (0)
+
+// Launch + count + check.  Usage: B2S_LAUNCH(ctx, kernel<T>, grid, block, smem, args...)
+#define B2S_LAUNCH(ctx, kern, grid, block, smem, ...)                                   \
+    do {                                                                                \
+        kern<<<(grid), (block), (smem), (ctx)->stream>>>(__VA_ARGS__);                  \
+        (ctx)->launches++;                                                              \
+        B2S_CUDA(ctx, cudaGetLastError());                                              \
+    } while (0)
+
+// Stream-ordered device allocation (cudaMallocAsync pool; freed on the same stream).
+struct DevBuf {
+    Ctx* ctx = nullptr;
+    void* p = nullptr;
+    size_t bytes = 0;
+    DevBuf() = default;
+    DevBuf(const DevBuf&) = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+    ~DevBuf() { release(); }
+    int32_t alloc(Ctx* c, size_t n) {
+        release();
+        ctx = c;
+        bytes = n;
+        if (n == 0) return B2S_OK;
+        cudaError_t e = cudaMallocAsync(&p, n, c->stream);
+        if (e != cudaSuccess) {
+            p = nullptr;
+            return fail(c, e == cudaErrorMemoryAllocation ? B2S_ERR_OOM : B2S_ERR_CUDA, "cudaMallocAsync(%zu): %s", n,
+                        cudaGetErrorString(e));
+        }
+        return B2S_OK;
+    }
+    void release() {
+        if (p) cudaFreeAsync(p, ctx->stream);
+        p = nullptr;
+        bytes = 0;
+    }
+    template <class T>
+    T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+// Bring a caller buffer onto the device (copy if it lives on the host, alias if already there).
+struct InBuf {
+    DevBuf own;
+    const void* dptr = nullptr;
+    int32_t bind(Ctx* c, const void* src, size_t bytes, int32_t mem) {
+        if (mem == B2S_MEM_DEVICE) { dptr = src; return B2S_OK; }
+        B2S_TRY(own.alloc(c, bytes));
+        if (bytes) B2S_CUDA(c, cudaMemcpyAsync(own.p, src, bytes, cudaMemcpyHostToDevice, c->stream));
+        dptr = own.p;
+        return B2S_OK;
+    }
+    template <class T>
+    const T* as() const { return reinterpret_cast<const T*>(dptr); }
+};
+
+inline unsigned cdiv(uint64_t a, uint64_t b) { return (unsigned)((a + b - 1) / b); }
+
+// Per-curve dispatch helper: F is a generic lambda taking a curve tag.
+template <class F>
+inline int32_t dispatch_curve(Ctx* c, F&& f) {
+    switch (c->curve) {
+        case B2S_CURVE_BLS12_381: return f(Bls12_381{});
+        case B2S_CURVE_BN254: return f(Bn254{});
+    }
+    return fail(c, B2S_ERR_INVALID_ARG, "unknown curve id %d", c->curve);
+}
+
+// ---- entry points implemented per translation unit (all take the ctx lock in api.cu) -----------
+int32_t ntt_run(Ctx* c, void* data_dev, uint32_t log_n, bool inverse, bool coset);
+void ntt_free_plans(Ctx* c);
+int32_t msm_run(Ctx* c, int group, const void* bases_dev, const void* scalars_dev, uint64_t n, bool scalars_mont,
+                void* out_xyzz_dev);
+int32_t group_sum_to_affine(Ctx* c, int group, const void* xyzz_dev, uint32_t count, void* out_affine_dev);
+
+}  // namespace b2s

@@ -23,9 +23,19 @@
 #if defined(__CUDACC__)
 #define B2S_HD __host__ __device__ __forceinline__
 #define B2S_D __device__ __forceinline__
+// Montgomery multiplication is ~300 (8 limbs) / ~650 (12 limbs) instructions.  Inlining it at every use
+// is right for the hot kernels (bucket accumulation, NTT butterflies) but makes the cold ones -- scalar
+// multiplications, G2 tails, test kernels -- take tens of minutes to compile, so a translation unit
+// opts in with B2S_INLINE_MUL; elsewhere the multiplication is one out-of-line function per field.
+#if defined(B2S_INLINE_MUL)
+#define B2S_MUL_ATTR __host__ __device__ __forceinline__
+#else
+#define B2S_MUL_ATTR __host__ __device__ __noinline__
+#endif
 #else
 #define B2S_HD inline
 #define B2S_D inline
+#define B2S_MUL_ATTR inline
 #endif
 
 namespace b2s {
@@ -212,7 +222,7 @@ struct Fp {
         O[N - 1] = cc::addc(O[N - 1], 0);
     }
 
-    B2S_HD friend Fp operator*(const Fp& a, const Fp& b) {
+    B2S_MUL_ATTR friend Fp operator*(const Fp& a, const Fp& b) {
         uint32_t E[N], O[N];
         // row 0: plain products
         {

@@ -1,0 +1,355 @@
+// K4: variable-base multi-scalar multiplication (Pippenger, signed radix-2^c windows) for G1 and G2.
+//
+// GPU counterpart of ark-ec `VariableBaseMSM::msm` / `msm_bigint` (upstream crate, not in
+// /root/reference; callers: ark-groth16 `create_proof_with_assignment`,
+// Appendix A.1).  The output is a group element, so after normalisation it is bit-identical to any
+// other correct MSM regardless of window size or summation order.
+//
+// Pipeline (all on the ctx stream, no host synchronisation inside):
+//   1 count     one thread per scalar: Montgomery -> canonical, signed digits, histogram of
+//               (window, |digit|) bucket sizes (global atomics, 4 B each)
+//   2 scan      exclusive prefix sums: bucket offsets in the sorted index array, and task offsets
+//               (a bucket of s points is cut into ceil(s / L) tasks so that no thread ever owns more
+//               than L points -- this is what keeps degenerate scalar distributions, e.g. the all-equal
+//               witness of the reference's DummyCircuit (relations/src/sr1cs/mod.rs:306-309), balanced)
+//   3 scatter   counting-sort the point indices (sign in bit 31) by bucket
+//   4 accumulate one thread per task: XYZZ accumulator += affine base, 8M+2S per point; bases are
+//               gathered from HBM (96 B / 192 B per point), everything else stays in registers
+//   5 reduce    buckets that were split: one CTA sums the task partials of a bucket (shared-memory tree)
+//   6 bucket sum per window sum_b b*B_b by segments: running sums over 16 buckets per thread, then
+//               seg_start * (segment total) by double-and-add; one CTA per window adds the segments
+//   7 horner    sum_w 2^(c w) S_w, one thread (255 doublings)
+//
+// Roofline: per (point, scalar) the algorithmic HBM traffic is 96+32 B (G1 BLS12-381), but each point
+// costs ceil(255/c) mixed additions of ~10 Fq multiplications = ~3000 wide IMADs; the kernel is
+// bound by the fma pipe by two orders of magnitude over HBM (DESIGN.md has the numbers).
+#include "msm_acc.cuh"
+
+namespace b2s {
+
+// ---- signed-digit recoding -------------------------------------------------------------------------
+// Digits of a canonical 256-bit scalar, least significant window first.  Windows other than the
+// last are recoded into [-2^(c-1), 2^(c-1)); the last keeps the carry (shape guarantees it fits B).
+struct DigitIter {
+    uint32_t k[8];
+    uint32_t carry;
+    __device__ __forceinline__ int32_t next(uint32_t w, uint32_t c, uint32_t nwin) {
+        const uint32_t bit = w * c;
+        const uint32_t word = bit >> 5, off = bit & 31;
+        uint64_t v = 0;
+        if (word < 8) v = k[word];
+        if (word + 1 < 8) v |= (uint64_t)k[word + 1] << 32;
+        uint32_t d = (uint32_t)((v >> off) & ((1u << c) - 1u)) + carry;
+        carry = 0;
+        if (w != nwin - 1 && d >= (1u << (c - 1))) {
+            carry = 1;
+            return (int32_t)d - (int32_t)(1u << c);
+        }
+        return (int32_t)d;
+    }
+};
+
+template <class Fr>
+__device__ __forceinline__ void load_scalar(DigitIter& it, const Fr* scalars, uint64_t i, bool mont) {
+    Fr s = ld_struct(scalars + i);
+    if (mont) s = s.from_mont();
+#pragma unroll
+    for (int j = 0; j < 8; j++) it.k[j] = s.v[j];
+    it.carry = 0;
+}
+
+template <class Fr>
+__global__ void msm_count_kernel(const Fr* __restrict__ scalars, uint64_t n, bool mont, MsmShape sh,
+                                 uint32_t* __restrict__ counts) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    DigitIter it;
+    load_scalar(it, scalars, i, mont);
+    for (uint32_t w = 0; w < sh.nwin; w++) {
+        const int32_t d = it.next(w, sh.c, sh.nwin);
+        if (d != 0) atomicAdd(&counts[w * sh.B + (uint32_t)(d < 0 ? -d : d) - 1], 1u);
+    }
+}
+
+// Single-CTA exclusive scans over G entries: offsets[g] (points) and task_off[g] (tasks); also
+// appends split buckets to `heavy` (list) with heavy[0] = count.
+__global__ void msm_scan_kernel(const uint32_t* __restrict__ counts, MsmShape sh, uint32_t* __restrict__ offsets,
+                                uint32_t* __restrict__ task_off, uint32_t* __restrict__ heavy) {
+    __shared__ uint32_t s_pts[1024], s_tsk[1024], s_hvy[1024];
+    const uint32_t tid = threadIdx.x, nt = blockDim.x;
+    const uint32_t per = (sh.G + nt - 1) / nt;
+    const uint32_t lo = min(tid * per, sh.G), hi = min(lo + per, sh.G);
+    uint32_t pts = 0, tsk = 0, hvy = 0;
+    for (uint32_t g = lo; g < hi; g++) {
+        const uint32_t s = counts[g];
+        const uint32_t t = (s + sh.L - 1) / sh.L;
+        pts += s; tsk += t; hvy += (t > 1);
+    }
+    s_pts[tid] = pts; s_tsk[tid] = tsk; s_hvy[tid] = hvy;
+    __syncthreads();
+    // Hillis-Steele inclusive scan over the per-thread totals
+    for (uint32_t d = 1; d < nt; d <<= 1) {
+        uint32_t a = 0, b = 0, h = 0;
+        if (tid >= d) { a = s_pts[tid - d]; b = s_tsk[tid - d]; h = s_hvy[tid - d]; }
+        __syncthreads();
+        s_pts[tid] += a; s_tsk[tid] += b; s_hvy[tid] += h;
+        __syncthreads();
+    }
+    uint32_t bp = s_pts[tid] - pts, bt = s_tsk[tid] - tsk, bh = s_hvy[tid] - hvy;
+    for (uint32_t g = lo; g < hi; g++) {
+        const uint32_t s = counts[g];
+        const uint32_t t = (s + sh.L - 1) / sh.L;
+        offsets[g] = bp; task_off[g] = bt;
+        if (t > 1) heavy[1 + bh++] = g;
+        bp += s; bt += t;
+    }
+    if (tid == nt - 1) {
+        offsets[sh.G] = s_pts[tid];
+        task_off[sh.G] = s_tsk[tid];
+        heavy[0] = s_hvy[tid];
+    }
+}
+
+template <class Fr>
+__global__ void msm_scatter_kernel(const Fr* __restrict__ scalars, uint64_t n, bool mont, MsmShape sh,
+                                   const uint32_t* __restrict__ offsets, uint32_t* __restrict__ cursor,
+                                   uint32_t* __restrict__ sorted) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    DigitIter it;
+    load_scalar(it, scalars, i, mont);
+    for (uint32_t w = 0; w < sh.nwin; w++) {
+        const int32_t d = it.next(w, sh.c, sh.nwin);
+        if (d == 0) continue;
+        const uint32_t g = w * sh.B + (uint32_t)(d < 0 ? -d : d) - 1;
+        const uint32_t pos = offsets[g] + atomicAdd(&cursor[g], 1u);
+        sorted[pos] = (uint32_t)i | (d < 0 ? 0x80000000u : 0u);
+    }
+}
+
+// Sum `count` XYZZ points with one CTA; result in out[0] (also used by the join of shard partials).
+template <class F>
+__device__ __forceinline__ XYZZ<F> cta_sum(const XYZZ<F>* __restrict__ pts, uint32_t count, XYZZ<F>* smem) {
+    XYZZ<F> acc = XYZZ<F>::identity();
+    for (uint32_t i = threadIdx.x; i < count; i += blockDim.x) {
+        XYZZ<F> v = ld_struct(pts + i);
+        acc.add(v);
+    }
+    smem[threadIdx.x] = acc;
+    __syncthreads();
+    for (uint32_t d = blockDim.x >> 1; d > 0; d >>= 1) {
+        if (threadIdx.x < d) {
+            XYZZ<F> a = smem[threadIdx.x];
+            a.add(smem[threadIdx.x + d]);
+            smem[threadIdx.x] = a;
+        }
+        __syncthreads();
+    }
+    return smem[0];
+}
+
+template <class F>
+__global__ void __launch_bounds__(MSM_RED_THREADS)
+msm_reduce_heavy_kernel(const uint32_t* __restrict__ heavy, const uint32_t* __restrict__ task_off,
+                        const XYZZ<F>* __restrict__ partials, XYZZ<F>* __restrict__ bucket_acc) {
+    extern __shared__ uint4 smem_raw[];
+    XYZZ<F>* smem = reinterpret_cast<XYZZ<F>*>(smem_raw);
+    const uint32_t nheavy = heavy[0];
+    for (uint32_t h = blockIdx.x; h < nheavy; h += gridDim.x) {
+        const uint32_t g = heavy[1 + h];
+        const uint32_t t0 = task_off[g], cnt = task_off[g + 1] - t0;
+        XYZZ<F> s = cta_sum(partials + t0, cnt, smem);
+        if (threadIdx.x == 0) st_struct(bucket_acc + g, s);
+        __syncthreads();
+    }
+}
+
+// k * p for a small non-negative integer k (double-and-add, most significant bit first)
+template <class F>
+__device__ __forceinline__ XYZZ<F> mul_small(const XYZZ<F>& p, uint32_t k) {
+    XYZZ<F> acc = XYZZ<F>::identity();
+    if (k == 0 || p.is_identity()) return acc;
+    for (int b = 31 - __clz(k); b >= 0; b--) {
+        acc = acc.dbl();
+        if ((k >> b) & 1) acc.add(p);
+    }
+    return acc;
+}
+
+// Segment sums: thread handles buckets [s0, s0 + MSM_SEG) of one window (bucket index b is 0-based,
+// weight b + 1):  sum (b+1) B_b = sum_{local} (j+1) B_{s0+j} + s0 * sum B_{s0+j}.
+template <class F>
+__global__ void __launch_bounds__(128)
+msm_bucket_segments_kernel(const XYZZ<F>* __restrict__ bucket_acc, MsmShape sh, XYZZ<F>* __restrict__ seg_out) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t segs_per_win = (sh.B + MSM_SEG - 1) / MSM_SEG;
+    if (t >= segs_per_win * sh.nwin) return;
+    const uint32_t w = t / segs_per_win, sg = t % segs_per_win;
+    const uint32_t s0 = sg * MSM_SEG, s1 = min(s0 + MSM_SEG, sh.B);
+    const XYZZ<F>* bk = bucket_acc + (size_t)w * sh.B;
+    XYZZ<F> run = XYZZ<F>::identity(), acc = XYZZ<F>::identity();
+    for (uint32_t j = s1; j-- > s0;) {
+        XYZZ<F> v = ld_struct(bk + j);
+        run.add(v);
+        acc.add(run);
+    }
+    if (s0 != 0) {
+        XYZZ<F> m = mul_small(run, s0);
+        acc.add(m);
+    }
+    st_struct(seg_out + t, acc);
+}
+
+// One CTA per window: S_w = sum of its segment results.
+template <class F>
+__global__ void __launch_bounds__(MSM_RED_THREADS)
+msm_window_sum_kernel(const XYZZ<F>* __restrict__ seg, uint32_t segs_per_win, XYZZ<F>* __restrict__ win_out) {
+    extern __shared__ uint4 smem_raw[];
+    XYZZ<F>* smem = reinterpret_cast<XYZZ<F>*>(smem_raw);
+    XYZZ<F> s = cta_sum(seg + (size_t)blockIdx.x * segs_per_win, segs_per_win, smem);
+    if (threadIdx.x == 0) st_struct(win_out + blockIdx.x, s);
+}
+
+// result = sum_w 2^(c w) S_w  (Horner from the top window).
+template <class F>
+__global__ void msm_horner_kernel(const XYZZ<F>* __restrict__ win, MsmShape sh, XYZZ<F>* __restrict__ out) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    XYZZ<F> acc = ld_struct(win + (sh.nwin - 1));
+    for (uint32_t w = sh.nwin - 1; w-- > 0;) {
+        for (uint32_t i = 0; i < sh.c; i++) acc = acc.dbl();
+        XYZZ<F> v = ld_struct(win + w);
+        acc.add(v);
+    }
+    st_struct(out, acc);
+}
+
+// sum of `count` XYZZ points -> affine (join of multi-GPU shard partials; final normalisation)
+template <class F>
+__global__ void __launch_bounds__(MSM_RED_THREADS)
+group_sum_affine_kernel(const XYZZ<F>* __restrict__ pts, uint32_t count, Affine<F>* __restrict__ out) {
+    extern __shared__ uint4 smem_raw[];
+    XYZZ<F>* smem = reinterpret_cast<XYZZ<F>*>(smem_raw);
+    XYZZ<F> s = cta_sum(pts, count, smem);
+    if (threadIdx.x == 0) {
+        Affine<F> a = s.to_affine();
+        st_struct(out, a);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+static uint32_t env_u32(const char* name, uint32_t dflt) {
+    const char* v = getenv(name);
+    return v ? (uint32_t)strtoul(v, nullptr, 10) : dflt;
+}
+
+static MsmShape msm_shape(uint64_t n, uint32_t scalar_bits) {
+    MsmShape sh{};
+    uint32_t logn = 0;
+    while ((1ull << logn) < n) logn++;
+    uint32_t c = logn > 6 ? logn - 6 : 1;
+    if (c < 5) c = 5;
+    if (c > 16) c = 16;
+    c = env_u32("B2S_MSM_C", c);
+    if (c < 2) c = 2;
+    if (c > 24) c = 24;
+    sh.c = c;
+    sh.nwin = (scalar_bits + c - 1) / c;
+    // the last window keeps the recoding carry: it must fit in 2^(c-1) buckets
+    if (scalar_bits - (sh.nwin - 1) * c >= c) sh.nwin += 1;
+    sh.B = 1u << (c - 1);
+    sh.G = sh.nwin * sh.B;
+    const uint64_t t_upper = (uint64_t)sh.nwin * n;
+    uint64_t L = t_upper >> 18;
+    if (L < 64) L = 64;
+    L = env_u32("B2S_MSM_L", (uint32_t)L);
+    sh.L = (uint32_t)L;
+    sh.max_tasks = t_upper / sh.L + sh.G + 1;
+    return sh;
+}
+
+template <class Curve, class F>
+static int32_t msm_run_t(Ctx* c, const void* bases_dev, const void* scalars_dev, uint64_t n, bool mont, void* out_dev) {
+    using Fr = typename Curve::Fr;
+    using Pt = XYZZ<F>;
+    if (n >= (1ull << 31)) return fail(c, B2S_ERR_INVALID_ARG, "msm: n = %llu exceeds 2^31 - 1", (unsigned long long)n);
+    Pt* out = reinterpret_cast<Pt*>(out_dev);
+    if (n == 0) {
+        B2S_CUDA(c, cudaMemsetAsync(out, 0, sizeof(Pt), c->stream));
+        return B2S_OK;
+    }
+    const MsmShape sh = msm_shape(n, Curve::FrP::BITS);
+    const Fr* scalars = reinterpret_cast<const Fr*>(scalars_dev);
+    const Affine<F>* bases = reinterpret_cast<const Affine<F>*>(bases_dev);
+
+    DevBuf ibuf, sorted, bucket_acc, partials, segs, wins;
+    // u32 arrays: counts[G] cursor[G] offsets[G+1] task_off[G+1] heavy[G+1]
+    const size_t ints = (size_t)5 * sh.G + 3;
+    B2S_TRY(ibuf.alloc(c, ints * sizeof(uint32_t)));
+    uint32_t* counts = ibuf.as<uint32_t>();
+    uint32_t* cursor = counts + sh.G;
+    uint32_t* offsets = cursor + sh.G;
+    uint32_t* task_off = offsets + sh.G + 1;
+    uint32_t* heavy = task_off + sh.G + 1;
+    B2S_CUDA(c, cudaMemsetAsync(counts, 0, (size_t)2 * sh.G * sizeof(uint32_t), c->stream));
+    B2S_TRY(sorted.alloc(c, (size_t)sh.nwin * n * sizeof(uint32_t)));
+    B2S_TRY(bucket_acc.alloc(c, (size_t)sh.G * sizeof(Pt)));
+    B2S_CUDA(c, cudaMemsetAsync(bucket_acc.p, 0, (size_t)sh.G * sizeof(Pt), c->stream));  // identity = zeros
+    B2S_TRY(partials.alloc(c, (size_t)sh.max_tasks * sizeof(Pt)));
+    const uint32_t segs_per_win = (sh.B + MSM_SEG - 1) / MSM_SEG;
+    B2S_TRY(segs.alloc(c, (size_t)segs_per_win * sh.nwin * sizeof(Pt)));
+    B2S_TRY(wins.alloc(c, (size_t)sh.nwin * sizeof(Pt)));
+
+    B2S_LAUNCH(c, msm_count_kernel<Fr>, cdiv(n, 256), 256, 0, scalars, n, mont, sh, counts);
+    B2S_LAUNCH(c, msm_scan_kernel, 1, 1024, 0, counts, sh, offsets, task_off, heavy);
+    B2S_LAUNCH(c, msm_scatter_kernel<Fr>, cdiv(n, 256), 256, 0, scalars, n, mont, sh, offsets, cursor, sorted.as<uint32_t>());
+    if (sizeof(F) == sizeof(typename Curve::Fq)) {
+        B2S_TRY(msm_accumulate_g1(c, bases, sorted.as<uint32_t>(), offsets, task_off, sh, bucket_acc.p, partials.p));
+    } else {
+        B2S_LAUNCH(c, msm_accumulate_kernel<F>, cdiv(sh.max_tasks, MSM_ACC_THREADS), MSM_ACC_THREADS, 0, bases,
+                   sorted.as<uint32_t>(), offsets, task_off, sh, bucket_acc.as<Pt>(), partials.as<Pt>());
+    }
+    const size_t red_smem = (size_t)MSM_RED_THREADS * sizeof(Pt);
+    static bool attr_done[2][2] = {{false, false}, {false, false}};
+    constexpr int gi = sizeof(F) == sizeof(typename Curve::Fq) ? 0 : 1;
+    if (!attr_done[Curve::id][gi]) {
+        B2S_CUDA(c, cudaFuncSetAttribute(msm_reduce_heavy_kernel<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)red_smem));
+        B2S_CUDA(c, cudaFuncSetAttribute(msm_window_sum_kernel<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)red_smem));
+        B2S_CUDA(c, cudaFuncSetAttribute(group_sum_affine_kernel<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)red_smem));
+        attr_done[Curve::id][gi] = true;
+    }
+    B2S_LAUNCH(c, msm_reduce_heavy_kernel<F>, 2 * c->sm_count, MSM_RED_THREADS, red_smem, heavy, task_off,
+               partials.as<Pt>(), bucket_acc.as<Pt>());
+    B2S_LAUNCH(c, msm_bucket_segments_kernel<F>, cdiv((uint64_t)segs_per_win * sh.nwin, 128), 128, 0,
+               bucket_acc.as<Pt>(), sh, segs.as<Pt>());
+    B2S_LAUNCH(c, msm_window_sum_kernel<F>, sh.nwin, MSM_RED_THREADS, red_smem, segs.as<Pt>(), segs_per_win, wins.as<Pt>());
+    B2S_LAUNCH(c, msm_horner_kernel<F>, 1, 32, 0, wins.as<Pt>(), sh, out);
+    return B2S_OK;
+}
+
+int32_t msm_run(Ctx* c, int group, const void* bases_dev, const void* scalars_dev, uint64_t n, bool scalars_mont,
+                void* out_xyzz_dev) {
+    return dispatch_curve(c, [&](auto curve) {
+        using C = decltype(curve);
+        if (group == 1) return msm_run_t<C, typename C::Fq>(c, bases_dev, scalars_dev, n, scalars_mont, out_xyzz_dev);
+        return msm_run_t<C, typename C::Fq2>(c, bases_dev, scalars_dev, n, scalars_mont, out_xyzz_dev);
+    });
+}
+
+template <class Curve, class F>
+static int32_t group_sum_t(Ctx* c, const void* xyzz_dev, uint32_t count, void* out_affine_dev) {
+    const size_t red_smem = (size_t)MSM_RED_THREADS * sizeof(XYZZ<F>);
+    B2S_CUDA(c, cudaFuncSetAttribute(group_sum_affine_kernel<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)red_smem));
+    B2S_LAUNCH(c, group_sum_affine_kernel<F>, 1, MSM_RED_THREADS, red_smem, reinterpret_cast<const XYZZ<F>*>(xyzz_dev),
+               count, reinterpret_cast<Affine<F>*>(out_affine_dev));
+    return B2S_OK;
+}
+
+int32_t group_sum_to_affine(Ctx* c, int group, const void* xyzz_dev, uint32_t count, void* out_affine_dev) {
+    return dispatch_curve(c, [&](auto curve) {
+        using C = decltype(curve);
+        if (group == 1) return group_sum_t<C, typename C::Fq>(c, xyzz_dev, count, out_affine_dev);
+        return group_sum_t<C, typename C::Fq2>(c, xyzz_dev, count, out_affine_dev);
+    });
+}
+
+}  // namespace b2s

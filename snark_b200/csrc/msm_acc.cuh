@@ -1,0 +1,105 @@
+// Bucket accumulation (step 4 of the MSM pipeline in msm.cu), shared between the translation unit that
+// compiles it with the field multiplication inlined (msm_acc_g1.cu: G1, the hot kernel of the whole
+// prover) and msm.cu (G2, out-of-line multiplication).
+#pragma once
+#include "common.cuh"
+
+namespace b2s {
+
+static constexpr int MSM_ACC_THREADS = 128;
+static constexpr int MSM_SEG = 16;          // buckets per thread in the bucket-sum kernel
+static constexpr int MSM_RED_THREADS = 128;
+
+struct MsmShape {
+    uint32_t c;        // window bits
+    uint32_t nwin;     // number of windows
+    uint32_t B;        // buckets per window = 2^(c-1)
+    uint32_t G;        // nwin * B
+    uint32_t L;        // max points per task
+    uint64_t max_tasks;
+};
+
+// ---- vector loads of whole structs ---------------------------------------------------------------
+template <class T>
+__device__ __forceinline__ T ld_struct(const T* p) {
+    static_assert(sizeof(T) % 16 == 0, "16-byte multiples only");
+    T r;
+    const uint4* s = reinterpret_cast<const uint4*>(p);
+    uint4* d = reinterpret_cast<uint4*>(&r);
+#pragma unroll
+    for (int i = 0; i < (int)(sizeof(T) / 16); i++) d[i] = __ldg(s + i);
+    return r;
+}
+template <class T>
+__device__ __forceinline__ void st_struct(T* p, const T& v) {
+    uint4* d = reinterpret_cast<uint4*>(p);
+    const uint4* s = reinterpret_cast<const uint4*>(&v);
+#pragma unroll
+    for (int i = 0; i < (int)(sizeof(T) / 16); i++) d[i] = s[i];
+}
+
+// rare paths of the mixed addition, kept out of line so the hot loop stays small
+template <class F>
+__device__ __noinline__ void madd_rare(XYZZ<F>& acc, const Affine<F>& q, bool r_is_zero) {
+    if (r_is_zero) acc = XYZZ<F>::dbl_affine(q);
+    else acc = XYZZ<F>::identity();
+}
+
+template <class F>
+__device__ __forceinline__ void madd(XYZZ<F>& acc, const Affine<F>& q) {
+    if (q.is_inf()) return;
+    if (acc.is_identity()) {
+        acc.x = q.x; acc.y = q.y; acc.zz = F::one(); acc.zzz = F::one();
+        return;
+    }
+    F p = q.x * acc.zz - acc.x;
+    F r = q.y * acc.zzz - acc.y;
+    if (p.is_zero()) { madd_rare(acc, q, r.is_zero()); return; }
+    F pp = p.sqr();
+    F ppp = p * pp;
+    F qv = acc.x * pp;
+    F x3 = r.sqr() - ppp - qv.dbl();
+    acc.y = r * (qv - x3) - acc.y * ppp;
+    acc.x = x3;
+    acc.zz = acc.zz * pp;
+    acc.zzz = acc.zzz * ppp;
+}
+
+// One thread per task.  Task t belongs to bucket g = upper_bound(task_off, t) - 1.
+template <class F>
+__global__ void __launch_bounds__(MSM_ACC_THREADS)
+msm_accumulate_kernel(const Affine<F>* __restrict__ bases, const uint32_t* __restrict__ sorted,
+                      const uint32_t* __restrict__ offsets, const uint32_t* __restrict__ task_off, MsmShape sh,
+                      XYZZ<F>* __restrict__ bucket_acc, XYZZ<F>* __restrict__ partials) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t total = task_off[sh.G];
+    if (t >= total) return;
+    // binary search: largest g with task_off[g] <= t  (empty buckets have task_off[g] == task_off[g+1])
+    uint32_t lo = 0, hi = sh.G;   // invariant: task_off[lo] <= t < task_off[hi]
+    while (hi - lo > 1) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (task_off[mid] <= t) lo = mid; else hi = mid;
+    }
+    const uint32_t g = lo;
+    const uint32_t k = t - task_off[g];
+    const uint32_t ntasks = task_off[g + 1] - task_off[g];
+    const uint32_t beg = offsets[g] + k * sh.L;
+    const uint32_t end = min(beg + sh.L, offsets[g + 1]);
+
+    XYZZ<F> acc = XYZZ<F>::identity();
+    for (uint32_t pos = beg; pos < end; pos++) {
+        const uint32_t e = sorted[pos];
+        Affine<F> q = ld_struct(bases + (e & 0x7fffffffu));
+        if (e >> 31) q.y = q.y.neg();
+        madd(acc, q);
+    }
+    if (ntasks == 1) st_struct(bucket_acc + g, acc);
+    else st_struct(partials + t, acc);
+}
+
+
+// G1 accumulate for the ctx's curve (msm_acc_g1.cu)
+int32_t msm_accumulate_g1(Ctx* c, const void* bases, const uint32_t* sorted, const uint32_t* offsets,
+                          const uint32_t* task_off, MsmShape sh, void* bucket_acc, void* partials);
+
+}  // namespace b2s

@@ -1,0 +1,20 @@
+// The hot kernel of the prover: G1 bucket accumulation with the Fq multiplication inlined (see
+// msm_acc.cuh / msm.cu for the algorithm).  Kept in its own translation unit so that only this
+// kernel pays the compile time of full inlining.
+#define B2S_INLINE_MUL 1
+#include "msm_acc.cuh"
+
+namespace b2s {
+
+int32_t msm_accumulate_g1(Ctx* c, const void* bases, const uint32_t* sorted, const uint32_t* offsets,
+                          const uint32_t* task_off, MsmShape sh, void* bucket_acc, void* partials) {
+    return dispatch_curve(c, [&](auto curve) {
+        using F = typename decltype(curve)::Fq;
+        B2S_LAUNCH(c, msm_accumulate_kernel<F>, cdiv(sh.max_tasks, MSM_ACC_THREADS), MSM_ACC_THREADS, 0,
+                   reinterpret_cast<const Affine<F>*>(bases), sorted, offsets, task_off, sh,
+                   reinterpret_cast<XYZZ<F>*>(bucket_acc), reinterpret_cast<XYZZ<F>*>(partials));
+        return (int32_t)B2S_OK;
+    });
+}
+
+}  // namespace b2s

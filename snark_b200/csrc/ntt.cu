@@ -1,0 +1,324 @@
+// K2: radix-2 NTT / iNTT / coset variants over the scalar field, natural order in and out.
+//
+// GPU counterpart of ark-poly `Radix2EvaluationDomain::{fft,ifft}_in_place` and `get_coset`
+// (upstream crate, not in /root/reference; consumer: ark-groth16
+// `witness_map`, Appendix A.2).  Exact field arithmetic, so any schedule gives identical bits.
+//
+// Schedule.  N = 2^log_n is factored N = R1 * R2 * R3 (up to three passes, R_i <= 2^10).  Viewing the
+// data as [P][R][M'] (P = product of earlier radices, M' = product of later ones), pass i runs, for every
+// (p, m), an R-point decimation-in-frequency NTT over the middle index in shared memory, multiplies
+// output k by the inter-pass twiddle w_N^(P*m*k) and stores it at [p][k][m].  After the last pass the
+// element at [k1][k2][k3] is X[k1 + R1*k2 + R1*R2*k3]; the last pass writes it straight to that index
+// (a tile holds chunks with consecutive k1, so those writes are contiguous runs), which removes the
+// separate bit-reversal pass.  Pass 1 streams data -> scratch, the middle pass works in place in
+// scratch, the last pass streams scratch -> data: 3 reads + 3 writes of N*32 B in total.
+//
+// Per element and transform: 32 B read + 32 B written once is the algorithmic traffic;
+// the arithmetic is log_n/2 butterfly multiplications + 2 twiddle multiplications per extra pass --
+// the kernel is bound by the integer-multiply (fma) pipe, not by HBM.
+//
+// Twiddles are never streamed as an N-entry table: w^e = lo[e mod 2^a] * hi[e >> a] from two
+// 2^(log_n/2)-entry tables (256 KiB at 2^24, L2/L1 resident).  Coset scaling (g^j on the way in,
+// g^-j * N^-1 on the way out) uses the same two-level scheme and is fused into the first / last pass.
+#define B2S_INLINE_MUL 1   // Fr butterflies: the multiplication is the kernel
+#include "common.cuh"
+
+namespace b2s {
+
+static constexpr int NTT_TILE_LOG = 10;   // elements per CTA tile (32 KiB of shared memory)
+static constexpr int NTT_THREADS = 256;
+static constexpr int NTT_MAX_RADIX_LOG = 10;
+
+struct PowTab {
+    const void* lo = nullptr;   // lo[i] = base^i,            i < 2^a
+    const void* hi = nullptr;   // hi[i] = c * base^(i 2^a),  i < 2^(log_n - a)   (c = optional constant)
+    uint32_t a = 0;
+};
+
+struct NttPlan {
+    uint32_t log_n = 0;
+    int npass = 0;
+    uint32_t radix[3] = {0, 0, 0};
+    DevBuf tables;     // all pow tables, contiguous
+    PowTab fwd, inv, coset_in, coset_out_scaled;
+    const void* n_inv = nullptr;   // one element: N^-1 (plain iNTT output scaling)
+};
+
+template <class Fr>
+__device__ __forceinline__ Fr gld(const Fr* p) {
+    static_assert(Fr::N == 8, "scalar fields are 8 x 32-bit limbs");
+    const uint4* q = reinterpret_cast<const uint4*>(p);
+    uint4 a = q[0], b = q[1];
+    Fr r;
+    r.v[0] = a.x; r.v[1] = a.y; r.v[2] = a.z; r.v[3] = a.w;
+    r.v[4] = b.x; r.v[5] = b.y; r.v[6] = b.z; r.v[7] = b.w;
+    return r;
+}
+template <class Fr>
+__device__ __forceinline__ void gst(Fr* p, const Fr& r) {
+    uint4* q = reinterpret_cast<uint4*>(p);
+    q[0] = make_uint4(r.v[0], r.v[1], r.v[2], r.v[3]);
+    q[1] = make_uint4(r.v[4], r.v[5], r.v[6], r.v[7]);
+}
+
+template <class Fr>
+__device__ __forceinline__ Fr pow_lookup(const PowTab& t, uint64_t e) {
+    const Fr* lo = reinterpret_cast<const Fr*>(t.lo);
+    const Fr* hi = reinterpret_cast<const Fr*>(t.hi);
+    Fr l = gld<Fr>(lo + (e & ((1ull << t.a) - 1)));
+    return l * gld<Fr>(hi + (e >> t.a));
+}
+
+// out[i] = c * base^(i * stride)
+template <class Fr>
+__global__ void pow_table_kernel(Fr* out, uint32_t count, Fr base, uint64_t stride, Fr c) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    out[i] = c * base.pow_u64((uint64_t)i * stride);
+}
+
+// ---- shared-memory tile: element (row j, column c) as two uint4 at pitch (2C+1) -----------------
+template <class Fr>
+__device__ __forceinline__ Fr tile_ld(const uint4* sm, uint32_t j, uint32_t c, uint32_t pitch) {
+    static_assert(Fr::N == 8, "scalar fields are 8 x 32-bit limbs");
+    const uint4* p = sm + j * pitch + 2 * c;
+    uint4 a = p[0], b = p[1];
+    Fr r;
+    r.v[0] = a.x; r.v[1] = a.y; r.v[2] = a.z; r.v[3] = a.w;
+    r.v[4] = b.x; r.v[5] = b.y; r.v[6] = b.z; r.v[7] = b.w;
+    return r;
+}
+template <class Fr>
+__device__ __forceinline__ void tile_st(uint4* sm, uint32_t j, uint32_t c, uint32_t pitch, const Fr& r) {
+    uint4* p = sm + j * pitch + 2 * c;
+    p[0] = make_uint4(r.v[0], r.v[1], r.v[2], r.v[3]);
+    p[1] = make_uint4(r.v[4], r.v[5], r.v[6], r.v[7]);
+}
+// R-point DIF NTT on every column of the tile; result row rho holds output bitrev(rho).
+template <class Fr>
+__device__ __forceinline__ void tile_dif(uint4* sm, const Fr* wtab, uint32_t log_r, uint32_t log_c, uint32_t pitch) {
+    const uint32_t C = 1u << log_c;
+    const uint32_t nbf = (1u << (log_r - 1)) << log_c;  // butterflies per stage
+    for (uint32_t s = 0; s < log_r; s++) {
+        const uint32_t lh = log_r - 1 - s;  // log2(half)
+        const uint32_t half = 1u << lh;
+        for (uint32_t b = threadIdx.x; b < nbf; b += blockDim.x) {
+            const uint32_t c = b & (C - 1);
+            const uint32_t t = b >> log_c;
+            const uint32_t pos = t & (half - 1);
+            const uint32_t j0 = ((t >> lh) << (lh + 1)) | pos;
+            const uint32_t j1 = j0 + half;
+            Fr x = tile_ld<Fr>(sm, j0, c, pitch);
+            Fr y = tile_ld<Fr>(sm, j1, c, pitch);
+            Fr d = x - y;
+            if (lh != 0) d = d * gld<Fr>(wtab + (pos << s));   // last stage: all twiddles are 1
+            tile_st<Fr>(sm, j0, c, pitch, x + y);
+            tile_st<Fr>(sm, j1, c, pitch, d);
+        }
+        __syncthreads();
+    }
+}
+
+__device__ __forceinline__ uint32_t bitrev(uint32_t x, uint32_t bits) { return bits ? (__brev(x) >> (32 - bits)) : 0; }
+
+struct PassArgs {
+    uint32_t log_n, log_r, log_m, log_p, log_c;
+    // final pass only
+    uint32_t log_r1, log_pp;
+    PowTab tw;        // w_N (or w_N^-1) powers
+    PowTab pre;       // input scaling by base^index (lo == nullptr: none)
+    PowTab post;      // output scaling by base^index * const (lo == nullptr: none)
+    const void* post_const;  // else: output scaling by one constant (nullptr: none)
+};
+
+// Non-final pass: sub-NTTs over a strided middle index, in-place positions.
+template <class Fr>
+__global__ void __launch_bounds__(NTT_THREADS) ntt_pass_strided(const Fr* __restrict__ src, Fr* __restrict__ dst, PassArgs a) {
+    extern __shared__ uint4 smem[];
+    const uint32_t R = 1u << a.log_r, C = 1u << a.log_c;
+    const uint32_t pitch = 2 * C + 1;
+    uint4* tile = smem;
+    Fr* wtab = reinterpret_cast<Fr*>(smem + (size_t)R * pitch + 1);  // keep 32 B alignment irrelevant: Fr is 4-byte aligned
+    const uint32_t tiles_per_p = 1u << (a.log_m - a.log_c);
+    const uint64_t p = blockIdx.x / tiles_per_p;
+    const uint64_t m0 = (uint64_t)(blockIdx.x % tiles_per_p) << a.log_c;
+
+    for (uint32_t e = threadIdx.x; e < R / 2; e += blockDim.x)
+        gst<Fr>(wtab + e, pow_lookup<Fr>(a.tw, (uint64_t)e << (a.log_n - a.log_r)));
+    for (uint32_t idx = threadIdx.x; idx < R * C; idx += blockDim.x) {
+        const uint32_t c = idx & (C - 1), j = idx >> a.log_c;
+        const uint64_t g = (((p << a.log_r) + j) << a.log_m) + m0 + c;
+        Fr v = gld<Fr>(src + g);
+        if (a.pre.lo) v = v * pow_lookup<Fr>(a.pre, g);
+        tile_st<Fr>(tile, j, c, pitch, v);
+    }
+    __syncthreads();
+    tile_dif<Fr>(tile, wtab, a.log_r, a.log_c, pitch);
+    for (uint32_t idx = threadIdx.x; idx < R * C; idx += blockDim.x) {
+        const uint32_t c = idx & (C - 1), rho = idx >> a.log_c;
+        const uint32_t k = bitrev(rho, a.log_r);
+        const uint64_t m = m0 + c;
+        Fr v = tile_ld<Fr>(tile, rho, c, pitch);
+        const uint64_t e = (m * k) << a.log_p;
+        if (e) v = v * pow_lookup<Fr>(a.tw, e);
+        gst<Fr>(dst + ((((p << a.log_r) + k) << a.log_m) + m), v);
+    }
+}
+
+// Final pass: contiguous R-point chunks; writes each result to its natural-order index.
+template <class Fr>
+__global__ void __launch_bounds__(NTT_THREADS) ntt_pass_final(const Fr* __restrict__ src, Fr* __restrict__ dst, PassArgs a) {
+    extern __shared__ uint4 smem[];
+    const uint32_t R = 1u << a.log_r, C = 1u << a.log_c;
+    const uint32_t pitch = 2 * C + 1;
+    uint4* tile = smem;
+    Fr* wtab = reinterpret_cast<Fr*>(smem + (size_t)R * pitch + 1);
+    const uint64_t PP = 1ull << a.log_pp;
+    const uint64_t pp = blockIdx.x & (PP - 1);
+    const uint64_t k1_0 = (uint64_t)(blockIdx.x >> a.log_pp) << a.log_c;
+
+    for (uint32_t e = threadIdx.x; e < R / 2; e += blockDim.x)
+        gst<Fr>(wtab + e, pow_lookup<Fr>(a.tw, (uint64_t)e << (a.log_n - a.log_r)));
+    for (uint32_t idx = threadIdx.x; idx < R * C; idx += blockDim.x) {
+        const uint32_t j = idx & (R - 1), cc = idx >> a.log_r;
+        const uint64_t chunk = ((k1_0 + cc) << a.log_pp) + pp;
+        const uint64_t g = (chunk << a.log_r) + j;
+        Fr v = gld<Fr>(src + g);
+        if (a.pre.lo) v = v * pow_lookup<Fr>(a.pre, g);
+        tile_st<Fr>(tile, j, cc, pitch, v);
+    }
+    __syncthreads();
+    tile_dif<Fr>(tile, wtab, a.log_r, a.log_c, pitch);
+    for (uint32_t idx = threadIdx.x; idx < R * C; idx += blockDim.x) {
+        const uint32_t cc = idx & (C - 1), rho = idx >> a.log_c;
+        const uint64_t k = bitrev(rho, a.log_r);
+        const uint64_t out = (k1_0 + cc) + ((pp + (k << a.log_pp)) << a.log_r1);
+        Fr v = tile_ld<Fr>(tile, rho, cc, pitch);
+        if (a.post.lo) v = v * pow_lookup<Fr>(a.post, out);
+        else if (a.post_const) v = v * gld<Fr>(reinterpret_cast<const Fr*>(a.post_const));
+        gst<Fr>(dst + out, v);
+    }
+}
+
+// -------------------------------------------------------------------------------------------
+#define B2S_FR_CONST(name, fn)          \
+    Fr name;                            \
+    for (int i_ = 0; i_ < Fr::N; i_++) name.v[i_] = FrP::fn(i_);
+
+template <class Curve>
+static int32_t build_plan(Ctx* c, uint32_t log_n, NttPlan** out) {
+    using Fr = typename Curve::Fr;
+    using FrP = typename Curve::FrP;
+    if (log_n > (uint32_t)FrP::TWO_ADICITY || log_n > 3 * NTT_MAX_RADIX_LOG - 3)
+        return fail(c, B2S_ERR_POLYNOMIAL_DEGREE_TOO_LARGE, "NTT size 2^%u unsupported", log_n);
+    NttPlan* pl = new NttPlan();
+    pl->log_n = log_n;
+    pl->npass = log_n <= NTT_MAX_RADIX_LOG ? 1 : (log_n <= 18 ? 2 : 3);
+    for (int i = 0; i < pl->npass; i++) pl->radix[i] = log_n / pl->npass + ((uint32_t)i < log_n % pl->npass ? 1 : 0);
+    const uint32_t a = (log_n + 1) / 2, b = log_n - a;
+    const uint32_t nlo = 1u << a, nhi = 1u << b;
+    // tables: fwd(lo,hi) inv(lo,hi) coset_in(lo,hi) coset_out(lo,hi) n_inv[1]
+    const size_t total = 4 * (size_t)(nlo + nhi) + 1;
+    int32_t st = pl->tables.alloc(c, total * sizeof(Fr));
+    if (st != B2S_OK) { delete pl; return st; }
+    Fr* base = pl->tables.as<Fr>();
+    // host-side constants (tiny host use of the field templates: a handful of multiplications)
+    B2S_FR_CONST(root, root) B2S_FR_CONST(root_inv, root_inv)
+    B2S_FR_CONST(g, gen) B2S_FR_CONST(g_inv, gen_inv) B2S_FR_CONST(half, half)
+    Fr w = root, wi = root_inv;
+    for (uint32_t i = log_n; i < (uint32_t)FrP::TWO_ADICITY; i++) { w = w.sqr(); wi = wi.sqr(); }
+    Fr n_inv = Fr::one();
+    for (uint32_t i = 0; i < log_n; i++) n_inv = n_inv * half;
+    const Fr one = Fr::one();
+    struct Spec { Fr bse; Fr c; PowTab* dst; } specs[4] = {
+        {w, one, &pl->fwd}, {wi, one, &pl->inv}, {g, one, &pl->coset_in}, {g_inv, n_inv, &pl->coset_out_scaled}};
+    Fr* cur = base;
+    for (auto& sp : specs) {
+        sp.dst->lo = cur; sp.dst->hi = cur + nlo; sp.dst->a = a;
+        pow_table_kernel<Fr><<<cdiv(nlo, 256), 256, 0, c->stream>>>(cur, nlo, sp.bse, 1, one);
+        pow_table_kernel<Fr><<<cdiv(nhi, 256), 256, 0, c->stream>>>(cur + nlo, nhi, sp.bse, 1ull << a, sp.c);
+        c->launches += 2;
+        cur += nlo + nhi;
+    }
+    pl->n_inv = cur;
+    pow_table_kernel<Fr><<<1, 32, 0, c->stream>>>(cur, 1, one, 0, n_inv);
+    c->launches += 1;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { delete pl; return fail(c, B2S_ERR_CUDA, "ntt table build: %s", cudaGetErrorString(e)); }
+    *out = pl;
+    return B2S_OK;
+}
+
+template <class Curve>
+static int32_t ntt_run_t(Ctx* c, void* data_dev, uint32_t log_n, bool inverse, bool coset) {
+    using Fr = typename Curve::Fr;
+    if (log_n == 0) return B2S_OK;  // size-1 transform is the identity (coset scaling g^0 = 1, 1/N = 1)
+    NttPlan* pl = nullptr;
+    auto it = c->ntt_plans.find(log_n);
+    if (it == c->ntt_plans.end()) {
+        B2S_TRY(build_plan<Curve>(c, log_n, &pl));
+        c->ntt_plans[log_n] = pl;
+    } else {
+        pl = it->second;
+    }
+    Fr* data = reinterpret_cast<Fr*>(data_dev);
+    DevBuf scratch;
+    if (pl->npass > 1) B2S_TRY(scratch.alloc(c, sizeof(Fr) << log_n));
+    Fr* tmp = scratch.as<Fr>();
+
+    PowTab none;
+    const PowTab tw = inverse ? pl->inv : pl->fwd;
+    const PowTab pre = (coset && !inverse) ? pl->coset_in : none;
+    const PowTab post = (inverse && coset) ? pl->coset_out_scaled : none;
+    const void* post_const = (inverse && !coset) ? pl->n_inv : nullptr;
+
+    static bool attr_set[2] = {false, false};
+    const size_t smem_bytes = ((size_t)(1u << NTT_TILE_LOG) * 2 + (1u << NTT_MAX_RADIX_LOG) + 2) * sizeof(uint4) +
+                              (size_t)(1u << (NTT_MAX_RADIX_LOG - 1)) * sizeof(Fr);
+    if (!attr_set[Curve::id]) {
+        B2S_CUDA(c, cudaFuncSetAttribute(ntt_pass_strided<Fr>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+        B2S_CUDA(c, cudaFuncSetAttribute(ntt_pass_final<Fr>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+        attr_set[Curve::id] = true;
+    }
+
+    uint32_t log_p = 0;
+    const Fr* src = data;
+    for (int i = 0; i < pl->npass; i++) {
+        const uint32_t log_r = pl->radix[i];
+        const bool last = (i == pl->npass - 1);
+        PassArgs a{};
+        a.log_n = log_n; a.log_r = log_r; a.log_p = log_p; a.log_m = log_n - log_p - log_r;
+        a.tw = tw;
+        a.pre = (i == 0) ? pre : none;
+        a.post = none;
+        a.post_const = nullptr;
+        if (!last) {
+            a.log_c = min((uint32_t)NTT_TILE_LOG - log_r, a.log_m);
+            Fr* dst = tmp;
+            const unsigned grid = 1u << (log_n - log_r - a.log_c);
+            B2S_LAUNCH(c, ntt_pass_strided<Fr>, grid, NTT_THREADS, smem_bytes, src, dst, a);
+            src = tmp;
+        } else {
+            a.log_r1 = (pl->npass == 1) ? 0 : pl->radix[0];
+            a.log_pp = log_p - a.log_r1;
+            a.log_c = min((uint32_t)NTT_TILE_LOG - min(log_r, (uint32_t)NTT_TILE_LOG), a.log_r1);
+            a.post = post;
+            a.post_const = post_const;
+            const unsigned grid = 1u << (log_n - log_r - a.log_c);
+            B2S_LAUNCH(c, ntt_pass_final<Fr>, grid, NTT_THREADS, smem_bytes, src, data, a);
+        }
+        log_p += log_r;
+    }
+    return B2S_OK;
+}
+
+int32_t ntt_run(Ctx* c, void* data_dev, uint32_t log_n, bool inverse, bool coset) {
+    return dispatch_curve(c, [&](auto curve) { return ntt_run_t<decltype(curve)>(c, data_dev, log_n, inverse, coset); });
+}
+
+void ntt_free_plans(Ctx* c) {
+    for (auto& kv : c->ntt_plans) delete kv.second;
+    c->ntt_plans.clear();
+}
+
+}  // namespace b2s

@@ -1,0 +1,270 @@
+"""ctypes binding of include/b200snark.h (one-to-one; see the header for semantics and the reference
+interfaces each entry point replaces)."""
+import ctypes
+import os
+from ctypes import POINTER, c_char_p, c_int32, c_uint32, c_uint64, c_void_p
+
+import numpy as np
+
+BLS12_381, BN254 = 0, 1
+MEM_HOST, MEM_DEVICE = 0, 1
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def lib_path():
+    return os.path.join(_HERE, "libb200snark.so")
+
+
+class B2SError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"b200snark error {code}: {msg}")
+        self.code = code
+
+
+class PkDesc(ctypes.Structure):
+    _fields_ = [
+        ("n_instance", c_uint64), ("n_witness", c_uint64), ("domain_size", c_uint64),
+        ("alpha_g1", c_void_p), ("beta_g1", c_void_p), ("delta_g1", c_void_p),
+        ("beta_g2", c_void_p), ("delta_g2", c_void_p),
+        ("a_query", c_void_p), ("a_off", c_uint64), ("a_len", c_uint64),
+        ("b_g1_query", c_void_p), ("b1_off", c_uint64), ("b1_len", c_uint64),
+        ("b_g2_query", c_void_p), ("b2_off", c_uint64), ("b2_len", c_uint64),
+        ("h_query", c_void_p), ("h_off", c_uint64), ("h_len", c_uint64),
+        ("l_query", c_void_p), ("l_off", c_uint64), ("l_len", c_uint64),
+    ]
+
+
+# name -> (restype, argtypes): every symbol include/b200snark.h declares
+SIGNATURES = {
+    "b2s_version": (c_char_p, []),
+    "b2s_ctx_create": (c_int32, [c_int32, c_int32, POINTER(c_void_p)]),
+    "b2s_ctx_destroy": (None, [c_void_p]),
+    "b2s_last_error": (c_char_p, [c_void_p]),
+    "b2s_sizes": (c_int32, [c_void_p, POINTER(c_uint32)]),
+    "b2s_launch_count": (c_uint64, [c_void_p]),
+    "b2s_sync": (c_int32, [c_void_p]),
+    "b2s_stream": (c_void_p, [c_void_p]),
+    "b2s_ntt": (c_int32, [c_void_p, c_void_p, c_uint32, c_int32, c_int32, c_int32]),
+    "b2s_msm_g1": (c_int32, [c_void_p, c_void_p, c_void_p, c_uint64, c_int32, c_int32, c_void_p]),
+    "b2s_msm_g2": (c_int32, [c_void_p, c_void_p, c_void_p, c_uint64, c_int32, c_int32, c_void_p]),
+    "b2s_msm_g1_partial": (c_int32, [c_void_p, c_void_p, c_void_p, c_uint64, c_int32, c_int32, c_void_p]),
+    "b2s_msm_g2_partial": (c_int32, [c_void_p, c_void_p, c_void_p, c_uint64, c_int32, c_int32, c_void_p]),
+    "b2s_g1_sum": (c_int32, [c_void_p, c_void_p, c_uint32, c_void_p]),
+    "b2s_g2_sum": (c_int32, [c_void_p, c_void_p, c_uint32, c_void_p]),
+    "b2s_r1cs_upload": (c_int32, [c_void_p, c_uint64, c_uint64, c_uint64, POINTER(c_void_p), POINTER(c_void_p),
+                                  POINTER(c_void_p), POINTER(c_void_p)]),
+    "b2s_r1cs_free": (None, [c_void_p, c_void_p]),
+    "b2s_spmv": (c_int32, [c_void_p, c_void_p, c_void_p, c_int32, c_void_p, c_void_p, c_void_p]),
+    "b2s_witness_map": (c_int32, [c_void_p, c_void_p, c_void_p, c_int32, c_void_p]),
+    "b2s_r1cs_domain_size": (c_uint64, [c_void_p]),
+    "b2s_pk_upload": (c_int32, [c_void_p, POINTER(PkDesc), c_int32, POINTER(c_void_p)]),
+    "b2s_pk_free": (None, [c_void_p, c_void_p]),
+    "b2s_groth16_prove": (c_int32, [c_void_p] * 10),
+    "b2s_groth16_prove_shard": (c_int32, [c_void_p] * 7),
+    "b2s_groth16_finish": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_uint32, c_void_p, c_void_p, c_void_p,
+                                     c_void_p, c_void_p]),
+    "b2s_fixed_base_g1": (c_int32, [c_void_p, c_void_p, c_uint64, c_int32, c_int32, c_void_p]),
+    "b2s_fixed_base_g2": (c_int32, [c_void_p, c_void_p, c_uint64, c_int32, c_int32, c_void_p]),
+    "b2s_field_op": (c_int32, [c_void_p, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_uint64]),
+    "b2s_group_op": (c_int32, [c_void_p, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_uint64]),
+}
+
+_lib = None
+
+
+def load_library():
+    """Load libb200snark.so and type every exported symbol.  Raises if the library is missing: there is
+    no Python or CPU substitute."""
+    global _lib
+    if _lib is None:
+        path = lib_path()
+        if not os.path.exists(path):
+            raise B2SError(-1, f"{path} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'`")
+        lib = ctypes.CDLL(path)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name)  # AttributeError if the header and the library disagree
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    return _lib
+
+
+def _ptr(x):
+    """Host numpy array or device torch tensor (or None / raw device address) -> (address, mem flag)."""
+    if x is None:
+        return None, MEM_HOST
+    if isinstance(x, np.ndarray):
+        assert x.flags["C_CONTIGUOUS"]
+        return x.ctypes.data, MEM_HOST
+    if isinstance(x, int):
+        return x, MEM_DEVICE
+    assert x.is_contiguous()  # torch tensor
+    return x.data_ptr(), (MEM_DEVICE if x.is_cuda else MEM_HOST)
+
+
+class Backend:
+    """One `b2s_ctx`: a curve bound to one GPU.  Buffers are numpy uint32/uint64 arrays (host) or
+    CUDA torch tensors (device), already in the C-ABI layout (Montgomery limbs)."""
+
+    def __init__(self, curve=BLS12_381, device=0):
+        self.h = None
+        self.lib = load_library()
+        h = c_void_p()
+        st = self.lib.b2s_ctx_create(curve, device, ctypes.byref(h))
+        if st != 0:
+            raise B2SError(st, "b2s_ctx_create failed" + (" (no sm_100 GPU visible)" if st == 17 else ""))
+        self.h = h
+        self.curve = curve
+        sz = (c_uint32 * 6)()
+        self.lib.b2s_sizes(self.h, sz)
+        self.fr_bytes, self.fq_bytes, self.g1_bytes, self.g2_bytes, self.g1x_bytes, self.g2x_bytes = list(sz)
+
+    def close(self):
+        if self.h:
+            self.lib.b2s_ctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, st):
+        if st != 0:
+            raise B2SError(st, self.lib.b2s_last_error(self.h).decode())
+
+    @property
+    def launches(self):
+        return int(self.lib.b2s_launch_count(self.h))
+
+    @property
+    def stream(self):
+        return self.lib.b2s_stream(self.h)
+
+    def sync(self):
+        self._ck(self.lib.b2s_sync(self.h))
+
+    # ---- kernels ------------------------------------------------------------------------------
+    def ntt(self, data, log_n, inverse=False, coset=False):
+        p, mem = _ptr(data)
+        self._ck(self.lib.b2s_ntt(self.h, p, log_n, int(inverse), int(coset), mem))
+        return data
+
+    def _msm(self, fn, out_bytes, bases, scalars, n, mont):
+        pb, mem = _ptr(bases)
+        ps, mem2 = _ptr(scalars)
+        assert n == 0 or mem == mem2
+        out = np.zeros(out_bytes // 4, dtype=np.uint32)
+        self._ck(fn(self.h, pb, ps, n, int(mont), mem, out.ctypes.data))
+        return out
+
+    def msm_g1(self, bases, scalars, n, mont=True):
+        return self._msm(self.lib.b2s_msm_g1, self.g1_bytes, bases, scalars, n, mont)
+
+    def msm_g2(self, bases, scalars, n, mont=True):
+        return self._msm(self.lib.b2s_msm_g2, self.g2_bytes, bases, scalars, n, mont)
+
+    def msm_g1_partial(self, bases, scalars, n, mont=True):
+        return self._msm(self.lib.b2s_msm_g1_partial, self.g1x_bytes, bases, scalars, n, mont)
+
+    def msm_g2_partial(self, bases, scalars, n, mont=True):
+        return self._msm(self.lib.b2s_msm_g2_partial, self.g2x_bytes, bases, scalars, n, mont)
+
+    def g1_sum(self, xyzz, count):
+        out = np.zeros(self.g1_bytes // 4, dtype=np.uint32)
+        self._ck(self.lib.b2s_g1_sum(self.h, xyzz.ctypes.data, count, out.ctypes.data))
+        return out
+
+    def g2_sum(self, xyzz, count):
+        out = np.zeros(self.g2_bytes // 4, dtype=np.uint32)
+        self._ck(self.lib.b2s_g2_sum(self.h, xyzz.ctypes.data, count, out.ctypes.data))
+        return out
+
+    def fixed_base(self, group, scalars, n, mont=True, out=None):
+        ps, mem = _ptr(scalars)
+        nbytes = (self.g1_bytes if group == 1 else self.g2_bytes) * n
+        if out is None:
+            assert mem == MEM_HOST
+            out = np.zeros(nbytes // 4, dtype=np.uint32)
+        po, mem_o = _ptr(out)
+        assert mem_o == mem
+        fn = self.lib.b2s_fixed_base_g1 if group == 1 else self.lib.b2s_fixed_base_g2
+        self._ck(fn(self.h, ps, n, int(mont), mem, po))
+        return out
+
+    def field_op(self, field, op, a, b):
+        out = np.zeros_like(a)
+        limbs = (self.fq_bytes if field == 0 else self.fr_bytes) // 4
+        self._ck(self.lib.b2s_field_op(self.h, field, op, a.ctypes.data, b.ctypes.data, out.ctypes.data, a.size // limbs))
+        return out
+
+    def group_op(self, group, op, a, b, k):
+        out = np.zeros_like(a)
+        limbs = (self.g1_bytes if group == 1 else self.g2_bytes) // 4
+        self._ck(self.lib.b2s_group_op(self.h, group, op, a.ctypes.data, b.ctypes.data, k.ctypes.data, out.ctypes.data,
+                                       a.size // limbs))
+        return out
+
+    # ---- R1CS ---------------------------------------------------------------------------------
+    def r1cs_upload(self, n_rows, n_instance, n_witness, csr):
+        """csr: three (row_ptr uint64[n_rows+1], col uint32[nnz], coeff uint32[nnz*8]) numpy triples."""
+        rp = (c_void_p * 3)(*[m[0].ctypes.data for m in csr])
+        col = (c_void_p * 3)(*[m[1].ctypes.data for m in csr])
+        co = (c_void_p * 3)(*[m[2].ctypes.data for m in csr])
+        h = c_void_p()
+        self._ck(self.lib.b2s_r1cs_upload(self.h, n_rows, n_instance, n_witness, rp, col, co, ctypes.byref(h)))
+        return h
+
+    def r1cs_free(self, m):
+        self.lib.b2s_r1cs_free(self.h, m)
+
+    def domain_size(self, m):
+        return int(self.lib.b2s_r1cs_domain_size(m))
+
+    def spmv(self, m, z, n_rows):
+        pz, mem = _ptr(z)
+        assert mem == MEM_HOST
+        outs = [np.zeros(n_rows * 8, dtype=np.uint32) for _ in range(3)]
+        self._ck(self.lib.b2s_spmv(self.h, m, pz, mem, *[o.ctypes.data for o in outs]))
+        return outs
+
+    def witness_map(self, m, z):
+        pz, mem = _ptr(z)
+        assert mem == MEM_HOST
+        h = np.zeros(self.domain_size(m) * 8, dtype=np.uint32)
+        self._ck(self.lib.b2s_witness_map(self.h, m, pz, mem, h.ctypes.data))
+        return h
+
+    # ---- Groth16 ------------------------------------------------------------------------------
+    def pk_upload(self, desc: PkDesc, mem=MEM_HOST):
+        h = c_void_p()
+        self._ck(self.lib.b2s_pk_upload(self.h, ctypes.byref(desc), mem, ctypes.byref(h)))
+        return h
+
+    def pk_free(self, pk):
+        self.lib.b2s_pk_free(self.h, pk)
+
+    def _proof_bufs(self):
+        return (np.zeros(self.g1_bytes // 4, dtype=np.uint32), np.zeros(self.g2_bytes // 4, dtype=np.uint32),
+                np.zeros(self.g1_bytes // 4, dtype=np.uint32))
+
+    def groth16_prove(self, pk, m, z_inst, z_wit, r, s):
+        a, b, c = self._proof_bufs()
+        self._ck(self.lib.b2s_groth16_prove(self.h, pk, m, _ptr(z_inst)[0], _ptr(z_wit)[0], r.ctypes.data, s.ctypes.data,
+                                            a.ctypes.data, b.ctypes.data, c.ctypes.data))
+        return a, b, c
+
+    def groth16_prove_shard(self, pk, m, z_inst, z_wit):
+        g1 = np.zeros(4 * self.g1x_bytes // 4, dtype=np.uint32)
+        g2 = np.zeros(self.g2x_bytes // 4, dtype=np.uint32)
+        self._ck(self.lib.b2s_groth16_prove_shard(self.h, pk, m, _ptr(z_inst)[0], _ptr(z_wit)[0], g1.ctypes.data,
+                                                  g2.ctypes.data))
+        return g1, g2
+
+    def groth16_finish(self, pk, g1_partials, g2_partials, n_shards, r, s):
+        a, b, c = self._proof_bufs()
+        self._ck(self.lib.b2s_groth16_finish(self.h, pk, g1_partials.ctypes.data, g2_partials.ctypes.data, n_shards,
+                                             r.ctypes.data, s.ctypes.data, a.ctypes.data, b.ctypes.data, c.ctypes.data))
+        return a, b, c

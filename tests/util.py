@@ -68,3 +68,61 @@ def pack_fr(curve, xs, mont=True):
 def unpack_fr(curve, arr, mont=True):
     Rinv = pow(1 << 256, -1, curve.r)
     return [(v * Rinv % curve.r) if mont else v for v in unpack_u32(arr, 8)]
+
+
+# ---- R1CS / proving-key marshalling (oracle objects -> C-ABI arrays) ----------------------------
+def csr_from_rows(curve, matrix):
+    """Oracle Matrix (rows of (coeff, col)) -> (row_ptr u64, col u32, coeff limbs u32) in Montgomery form."""
+    row_ptr = np.zeros(len(matrix) + 1, dtype=np.uint64)
+    cols, coeffs = [], []
+    for i, row in enumerate(matrix):
+        for c, col in row:
+            cols.append(col)
+            coeffs.append(c)
+        row_ptr[i + 1] = len(cols)
+    col = np.array(cols, dtype=np.uint32) if cols else np.zeros(0, dtype=np.uint32)
+    co = pack_fr(curve, coeffs) if coeffs else np.zeros(0, dtype=np.uint32)
+    return row_ptr, col, co
+
+
+def make_pk_desc(curve, pk, keep):
+    """Oracle ProvingKey -> snark_b200.lib.PkDesc (full key).  `keep` receives the numpy arrays so they
+    outlive the descriptor."""
+    from snark_b200.lib import PkDesc
+
+    d = PkDesc()
+    d.n_instance = pk.num_instance
+    d.n_witness = len(pk.l_query)
+    d.domain_size = pk.domain
+
+    def put(name, group, pts):
+        arr = pack_points(curve, group, pts)
+        keep.append(arr)
+        setattr(d, name, arr.ctypes.data)
+        return len(pts)
+
+    put("alpha_g1", 1, [pk.alpha_g1]); put("beta_g1", 1, [pk.beta_g1]); put("delta_g1", 1, [pk.delta_g1])
+    put("beta_g2", 2, [pk.beta_g2]); put("delta_g2", 2, [pk.delta_g2])
+    d.a_len = put("a_query", 1, pk.a_query)
+    d.b1_len = put("b_g1_query", 1, pk.b_g1_query)
+    d.b2_len = put("b_g2_query", 2, pk.b_g2_query)
+    d.h_len = put("h_query", 1, pk.h_query)
+    d.l_len = put("l_query", 1, pk.l_query)
+    return d
+
+
+def random_fr_limbs(rng, n, bits=254):
+    """n random field elements as raw limbs (uint32[n*8]), uniform in [0, 2^bits) (< r for both curves)."""
+    a = rng.integers(0, 1 << 32, size=(n, 8), dtype=np.uint64).astype(np.uint32)
+    top = bits - 224
+    a[:, 7] &= np.uint32((1 << top) - 1)
+    return a.reshape(-1)
+
+
+def limbs_to_ints(arr, n=8):
+    """uint32[count*n] -> list of Python ints (vectorised per limb)."""
+    a = np.asarray(arr, dtype=np.uint32).reshape(-1, n).astype(object)
+    acc = a[:, 0].copy()
+    for j in range(1, n):
+        acc = acc + (a[:, j] << (32 * j))
+    return list(acc)
