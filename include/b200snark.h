@@ -83,6 +83,12 @@ int32_t b2s_sync(b2s_ctx* ctx);
 /* the CUDA stream (cudaStream_t) the ctx launches on, for CUDA-event timing by the harness */
 void* b2s_stream(b2s_ctx* ctx);
 
+/* Per-kernel device timing: when enabled, every kernel launch of this ctx is bracketed by CUDA events on
+ * the ctx stream.  b2s_profile_report synchronises, writes one line per kernel name
+ * ("<name>\t<launches>\t<total_ms>\n", NUL terminated, truncated to cap) and clears the records. */
+int32_t b2s_profile_enable(b2s_ctx* ctx, int32_t on);
+int32_t b2s_profile_report(b2s_ctx* ctx, char* buf, uint64_t cap);
+
 /* ---- K2: radix-2 NTT over Fr (ark-poly Radix2EvaluationDomain::{fft,ifft}_in_place, get_coset) ----
  * In place on 2^log_n Montgomery-form elements, natural order in and out.
  *   inverse = 0: X[i] = sum_j x[j] (c w^i)^j            inverse = 1: the inverse map (includes 1/N)
@@ -146,10 +152,16 @@ void b2s_pk_free(b2s_ctx* ctx, b2s_pk* pk);
 int32_t b2s_groth16_prove(b2s_ctx* ctx, const b2s_pk* pk, const b2s_r1cs* m, const void* z_instance,
                           const void* z_witness, const void* r, const void* s, void* out_a_g1, void* out_b_g2,
                           void* out_c_g1);
+/* Same, with z = instance || witness already resident on the GPU (n_instance + n_witness elements). */
+int32_t b2s_groth16_prove_resident(b2s_ctx* ctx, const b2s_pk* pk, const b2s_r1cs* m, const void* z_dev, const void* r,
+                                   const void* s, void* out_a_g1, void* out_b_g2, void* out_c_g1);
 /* Shard step for multi-GPU: computes this shard's five MSM partial sums
  *   out_partials = [ h_acc, l_acc, a_acc, b1_acc ] (4 G1 XYZZ) and out_b2_partial (1 G2 XYZZ), HOST. */
 int32_t b2s_groth16_prove_shard(b2s_ctx* ctx, const b2s_pk* pk, const b2s_r1cs* m, const void* z_instance,
                                 const void* z_witness, void* out_g1_partials, void* out_g2_partial);
+/* Same with z resident on the GPU. */
+int32_t b2s_groth16_prove_shard_resident(b2s_ctx* ctx, const b2s_pk* pk, const b2s_r1cs* m, const void* z_dev,
+                                         void* out_g1_partials, void* out_g2_partial);
 /* Join: sums the per-shard partials (n_shards x 4 G1 XYZZ, n_shards G2 XYZZ) and applies the r/s epilogue. */
 int32_t b2s_groth16_finish(b2s_ctx* ctx, const b2s_pk* pk, const void* g1_partials, const void* g2_partials,
                            uint32_t n_shards, const void* r, const void* s, void* out_a_g1, void* out_b_g2,

@@ -16,7 +16,7 @@ prover hot path and the in-tree matrix x witness products:
   * BenchCircuit (shape only)          relations/examples/bench.rs:22-83
 
 Pinned by the reference's golden matrices: circuit2.rs:21-43 and circuit1.rs:28-61
-(tests/test_oracle_r1cs.py).
+(tests/test_oracle_py.py).
 """
 from .params import Curve
 
@@ -137,7 +137,9 @@ class ConstraintSystem:
         self.num_witness_variables = 0
         self.lcs = [[]]                           # lc 0 == zero LC (constraint_system.rs:112)
         self.lc_assignment = [0]
-        self.constraints = []                     # list of (a_var, b_var, c_var)
+        self.constraints = []                     # R1CS predicate: list of (a_var, b_var, c_var)
+        # other predicates (predicate/mod.rs:81-94): label -> dict(arity, terms, constraints)
+        self.predicates = {}
 
     # -- allocation (constraint_system.rs:591-617) ------------------------
     def new_input_variable(self, f):
@@ -187,7 +189,39 @@ class ConstraintSystem:
         self.constraints.append((self.new_lc(a), self.new_lc(b), self.new_lc(c)))
 
     def num_constraints(self):
-        return len(self.constraints)
+        return len(self.constraints) + sum(len(p["constraints"]) for p in self.predicates.values())
+
+    # -- generic polynomial predicates (predicate/mod.rs:96-174, polynomial_constraint.rs:16-66) ------
+    def register_predicate(self, label, arity, terms):
+        """terms: [(coeff, [(argument index, exponent), ...])]; satisfied iff the polynomial is 0."""
+        self.predicates[label] = {"arity": arity, "terms": terms, "constraints": []}
+
+    def enforce_constraint(self, label, lcs):
+        if label == "R1CS":
+            return self.enforce_r1cs_constraint(*lcs)
+        if label not in self.predicates:
+            raise SynthesisError("PredicateNotFound")
+        pred = self.predicates[label]
+        if len(lcs) != pred["arity"]:
+            raise SynthesisError("ArityMismatch")
+        pred["constraints"].append(tuple(self.new_lc(l) for l in lcs))
+
+    def _lc_value(self, v):
+        val = self.assigned_value(v)
+        if val is None:
+            val = sum(c * self.assigned_value(x) for c, x in self.get_lc(v)) % self.r
+        return val
+
+    def to_matrices_all(self):
+        """BTreeMap<Label, Vec<Matrix>> of constraint_system.rs:768-774 (labels in lexicographic order)."""
+        out = {"R1CS": self.to_matrices()}
+        for label, pred in self.predicates.items():
+            mats = [[] for _ in range(pred["arity"])]
+            for cons in pred["constraints"]:
+                for k, v in enumerate(cons):
+                    mats[k].append(self.make_row(self.get_lc(v)))
+            out[label] = mats
+        return dict(sorted(out.items()))
 
     # -- finalize (constraint_system.rs:691-758) --------------------------
     def finalize(self):
@@ -243,7 +277,19 @@ class ConstraintSystem:
                     val = sum(c * self.assigned_value(x) for c, x in self.get_lc(v)) % self.r
                 vals.append(val)
             if (vals[0] * vals[1] - vals[2]) % self.r != 0:
-                return i
+                return ("R1CS", i)
+        for label in sorted(self.predicates):
+            pred = self.predicates[label]
+            for i, cons in enumerate(pred["constraints"]):
+                x = [self._lc_value(v) for v in cons]
+                acc = 0
+                for coeff, mono in pred["terms"]:
+                    t = coeff
+                    for idx, e in mono:
+                        t = t * pow(x[idx], e, self.r)
+                    acc += t
+                if acc % self.r != 0:
+                    return (label, i)
         return None
 
     def is_satisfied(self):
@@ -288,6 +334,35 @@ def circuit2(curve: Curve, a, b, c):
     cs.enforce_r1cs_constraint(L() + V_ONE, L() + e, L() + e)
     return cs
 
+
+def circuit1(curve: Curve, x, w):
+    """gr1cs/tests/circuit1.rs:63-164: three polynomial predicates; x = (x1..x5), w = (w1..w8)."""
+    r = curve.r
+    cs = ConstraintSystem(curve)
+    xv = [cs.new_input_variable(lambda v=v: v) for v in x]
+    wv = [cs.new_witness_variable(lambda v=v: v) for v in w]
+    x1, x2, x3, x4, x5 = xv
+    w1, w2, w3, w4, w5, w6, _w7, w8 = wv
+    cs.register_predicate("poly-predicate-A", 4, [(1, [(0, 1), (1, 1)]), (3, [(2, 2)]), (r - 1, [(3, 1)])])
+    cs.register_predicate("poly-predicate-B", 3, [(7, [(1, 1)]), (1, [(0, 3)]), (r - 1, [(2, 1)])])
+    cs.register_predicate("poly-predicate-C", 3, [(1, [(0, 1), (1, 1)]), (r - 1, [(2, 1)])])
+    L = lambda: LinearCombination(r)
+    cs.enforce_constraint("poly-predicate-A", [L() + x1, L() + x2, L() + x3, L() + w4])
+    cs.enforce_constraint("poly-predicate-B", [L() + x4, L() + w1, L() + w5])
+    cs.enforce_constraint("poly-predicate-B", [L() + w5, L() + w6, L() + w8])
+    cs.enforce_constraint("poly-predicate-C", [L() + w2, L() + w3, L() + w6])
+    cs.enforce_constraint("poly-predicate-C", [L() + w5 + w4, L() + w8, L() + x5])
+    return cs
+
+
+CIRCUIT1_GOLDEN = {  # circuit1.rs:28-61
+    "R1CS": [[], [], []],
+    "poly-predicate-A": [[[(1, 1)]], [[(1, 2)]], [[(1, 3)]], [[(1, 9)]]],
+    "poly-predicate-B": [[[(1, 4)], [(1, 10)]], [[(1, 6)], [(1, 11)]], [[(1, 10)], [(1, 13)]]],
+    "poly-predicate-C": [[[(1, 7)], [(1, 9), (1, 10)]], [[(1, 8)], [(1, 13)]], [[(1, 11)], [(1, 5)]]],
+}
+CIRCUIT1_SAT = ((1, 2, 3, 0, 1255254), (4, 2, 5, 29, 28, 10, 57, 22022))       # tests/mod.rs:19-33
+CIRCUIT1_UNSAT = ((4, 2, 3, 0, 1255254), (4, 2, 5, 29, 28, 10, 57, 22022))     # tests/mod.rs:57-71
 
 CIRCUIT2_GOLDEN = [  # circuit2.rs:21-43
     [[(1, 1)], [(1, 1)], [(1, 0)]],
@@ -352,10 +427,9 @@ def bench_circuit(curve: Curve, num_constraints, seed=0):
     """BenchCircuit shape (examples/bench.rs:22-83): rows of 1..10 unit-coefficient terms drawn
     from the last <= 10 allocated variables, every other A row extended by an inlined LC of the same
     size, C rows a single variable; 3 new witnesses per constraint.  The PRNG differs from the
-    reference's StdRng, so only the *shape* matches.  Witness values are chosen so that the system
-    is satisfied: each constraint's fresh variable v1 is forced to make C = A*B impossible in
-    general, so instead the returned assignment is checked by `is_satisfied` in tests only for the
-    satisfiable variant (`satisfiable=True` rewrites C rows to a fresh product witness)."""
+    reference's StdRng, so only the *shape* matches.  Unlike the reference bench (which never checks
+    satisfaction and points C at an existing variable), the C row is the first of the three fresh
+    witnesses, assigned the product A_i(z) * B_i(z), so the system is satisfiable and usable for proofs."""
     r = curve.r
     cs = ConstraintSystem(curve)
     rng = XorShift64(seed)

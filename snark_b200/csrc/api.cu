@@ -213,6 +213,13 @@ int32_t b2s_fixed_base_g2(b2s_ctx* ctx, const void* scalars, uint64_t n, int32_t
 }  // extern "C"
 
 // ---- R1CS / witness map / Groth16 --------------------------------------------------------------
+static int32_t check_full_key(b2s_ctx* ctx, const b2s_pk* pk) {
+    const uint64_t n_vars = pk->n_instance + pk->n_witness;
+    if (pk->a_len != n_vars || pk->b1_len != n_vars || pk->b2_len != n_vars || pk->l_len != pk->n_witness ||
+        pk->h_len + 1 != pk->domain_size)
+        return fail(ctx, B2S_ERR_MALFORMED_VK, "prove: needs a full (unsharded) proving key");
+    return B2S_OK;
+}
 extern "C" {
 
 int32_t b2s_r1cs_upload(b2s_ctx* ctx, uint64_t n_rows, uint64_t n_instance, uint64_t n_witness,
@@ -298,7 +305,7 @@ int32_t b2s_groth16_prove_shard(b2s_ctx* ctx, const b2s_pk* pk, const b2s_r1cs* 
     DevBuf g1, g2;
     B2S_TRY(g1.alloc(ctx, 4 * sz[4]));
     B2S_TRY(g2.alloc(ctx, sz[5]));
-    B2S_TRY(groth16_shard(ctx, pk, m, z_instance, z_witness, g1.p, g2.p));
+    B2S_TRY(groth16_shard(ctx, pk, m, z_instance, z_witness, nullptr, g1.p, g2.p));
     B2S_CUDA(ctx, cudaMemcpyAsync(out_g1_partials, g1.p, 4 * sz[4], cudaMemcpyDeviceToHost, ctx->stream));
     B2S_CUDA(ctx, cudaMemcpyAsync(out_g2_partial, g2.p, sz[5], cudaMemcpyDeviceToHost, ctx->stream));
     B2S_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -325,17 +332,81 @@ int32_t b2s_groth16_prove(b2s_ctx* ctx, const b2s_pk* pk, const b2s_r1cs* m, con
     if (!pk || !m) return fail(ctx, B2S_ERR_MISSING_CS, "prove: null key or matrices");
     if (!z_instance || (!z_witness && m->n_witness) || !r || !s) return fail(ctx, B2S_ERR_ASSIGNMENT_MISSING, "prove: null assignment");
     if (!out_a_g1 || !out_b_g2 || !out_c_g1) return fail(ctx, B2S_ERR_INVALID_ARG, "prove: null output");
-    const uint64_t n_vars = pk->n_instance + pk->n_witness;
-    if (pk->a_len != n_vars || pk->b1_len != n_vars || pk->b2_len != n_vars || pk->l_len != pk->n_witness ||
-        pk->h_len + 1 != pk->domain_size)
-        return fail(ctx, B2S_ERR_MALFORMED_VK, "prove: needs a full (unsharded) proving key");
+    B2S_TRY(check_full_key(ctx, pk));
     uint32_t sz[6];
     sizes_for(ctx->curve, sz);
     DevBuf g1, g2;
     B2S_TRY(g1.alloc(ctx, 4 * sz[4]));
     B2S_TRY(g2.alloc(ctx, sz[5]));
-    B2S_TRY(groth16_shard(ctx, pk, m, z_instance, z_witness, g1.p, g2.p));
+    B2S_TRY(groth16_shard(ctx, pk, m, z_instance, z_witness, nullptr, g1.p, g2.p));
     return groth16_finish(ctx, pk, g1.p, g2.p, 1, r, s, out_a_g1, out_b_g2, out_c_g1);
+}
+
+
+int32_t b2s_groth16_prove_resident(b2s_ctx* ctx, const b2s_pk* pk, const b2s_r1cs* m, const void* z_dev, const void* r,
+                                   const void* s, void* out_a_g1, void* out_b_g2, void* out_c_g1) {
+    LOCK(ctx);
+    if (!pk || !m) return fail(ctx, B2S_ERR_MISSING_CS, "prove: null key or matrices");
+    if (!z_dev || !r || !s) return fail(ctx, B2S_ERR_ASSIGNMENT_MISSING, "prove: null assignment");
+    if (!out_a_g1 || !out_b_g2 || !out_c_g1) return fail(ctx, B2S_ERR_INVALID_ARG, "prove: null output");
+    B2S_TRY(check_full_key(ctx, pk));
+    uint32_t sz[6];
+    sizes_for(ctx->curve, sz);
+    DevBuf g1, g2;
+    B2S_TRY(g1.alloc(ctx, 4 * sz[4]));
+    B2S_TRY(g2.alloc(ctx, sz[5]));
+    B2S_TRY(groth16_shard(ctx, pk, m, nullptr, nullptr, z_dev, g1.p, g2.p));
+    return groth16_finish(ctx, pk, g1.p, g2.p, 1, r, s, out_a_g1, out_b_g2, out_c_g1);
+}
+
+int32_t b2s_groth16_prove_shard_resident(b2s_ctx* ctx, const b2s_pk* pk, const b2s_r1cs* m, const void* z_dev,
+                                         void* out_g1_partials, void* out_g2_partial) {
+    LOCK(ctx);
+    if (!pk || !m) return fail(ctx, B2S_ERR_MISSING_CS, "prove_shard: null key or matrices");
+    if (!z_dev || !out_g1_partials || !out_g2_partial) return fail(ctx, B2S_ERR_ASSIGNMENT_MISSING, "prove_shard: null argument");
+    uint32_t sz[6];
+    sizes_for(ctx->curve, sz);
+    DevBuf g1, g2;
+    B2S_TRY(g1.alloc(ctx, 4 * sz[4]));
+    B2S_TRY(g2.alloc(ctx, sz[5]));
+    B2S_TRY(groth16_shard(ctx, pk, m, nullptr, nullptr, z_dev, g1.p, g2.p));
+    B2S_CUDA(ctx, cudaMemcpyAsync(out_g1_partials, g1.p, 4 * sz[4], cudaMemcpyDeviceToHost, ctx->stream));
+    B2S_CUDA(ctx, cudaMemcpyAsync(out_g2_partial, g2.p, sz[5], cudaMemcpyDeviceToHost, ctx->stream));
+    B2S_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return B2S_OK;
+}
+
+int32_t b2s_profile_enable(b2s_ctx* ctx, int32_t on) {
+    LOCK(ctx);
+    ctx->profiling = on != 0;
+    return B2S_OK;
+}
+
+int32_t b2s_profile_report(b2s_ctx* ctx, char* buf, uint64_t cap) {
+    LOCK(ctx);
+    if (!buf || cap == 0) return fail(ctx, B2S_ERR_INVALID_ARG, "profile_report: null buffer");
+    B2S_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    std::map<std::string, std::pair<uint64_t, double>> agg;
+    for (auto& r : ctx->prof) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, r.e0, r.e1);
+        auto& a = agg[r.name];
+        a.first++;
+        a.second += ms;
+        cudaEventDestroy(r.e0);
+        cudaEventDestroy(r.e1);
+    }
+    ctx->prof.clear();
+    std::string out;
+    char line[256];
+    for (auto& kv : agg) {
+        snprintf(line, sizeof(line), "%s\t%llu\t%.6f\n", kv.first.c_str(), (unsigned long long)kv.second.first, kv.second.second);
+        out += line;
+    }
+    const size_t nn = out.size() < cap - 1 ? out.size() : (size_t)cap - 1;
+    memcpy(buf, out.data(), nn);
+    buf[nn] = 0;
+    return B2S_OK;
 }
 
 }  // extern "C"

@@ -28,6 +28,10 @@ struct Ctx {
     uint64_t launches = 0;
     int sm_count = 148;
     std::map<uint32_t, NttPlan*> ntt_plans;   // keyed by log_n
+    // optional per-kernel timing (b2s_profile_*): CUDA events around every launch on `stream`
+    bool profiling = false;
+    struct ProfRec { const char* name; cudaEvent_t e0, e1; };
+    std::vector<ProfRec> prof;
     void* fixed_base_tables[2] = {nullptr, nullptr};  // G1 / G2 window tables (setup.cu)
 };
 
@@ -58,8 +62,18 @@ inline int32_t fail(Ctx* c, int32_t code, const char* fmt, ...) {
 // Launch + count + check.  Usage: B2S_LAUNCH(ctx, kernel<T>, grid, block, smem, args...)
 #define B2S_LAUNCH(ctx, kern, grid, block, smem, ...)                                   \
     do {                                                                                \
+        ::b2s::Ctx::ProfRec pr__{#kern, nullptr, nullptr};                              \
+        if ((ctx)->profiling) {                                                         \
+            cudaEventCreate(&pr__.e0);                                                  \
+            cudaEventCreate(&pr__.e1);                                                  \
+            cudaEventRecord(pr__.e0, (ctx)->stream);                                    \
+        }                                                                               \
         kern<<<(grid), (block), (smem), (ctx)->stream>>>(__VA_ARGS__);                  \
         (ctx)->launches++;                                                              \
+        if ((ctx)->profiling) {                                                         \
+            cudaEventRecord(pr__.e1, (ctx)->stream);                                    \
+            (ctx)->prof.push_back(pr__);                                                \
+        }                                                                               \
         B2S_CUDA(ctx, cudaGetLastError());                                              \
     } while (0)
 

@@ -133,8 +133,8 @@ int32_t pk_upload(Ctx* c, const b2s_pk_desc* d, int32_t mem, b2s_pk** out) {
 }
 
 template <class Curve>
-static int32_t shard_t(Ctx* c, const b2s_pk* pk, const b2s_r1cs* m, const void* z_inst, const void* z_wit, void* g1_out,
-                       void* g2_out) {
+static int32_t shard_t(Ctx* c, const b2s_pk* pk, const b2s_r1cs* m, const void* z_inst, const void* z_wit, const void* z_dev,
+                       void* g1_out, void* g2_out) {
     using Fr = typename Curve::Fr;
     using P1 = XYZZ<typename Curve::Fq>;
     const uint64_t N = 1ull << m->log_domain;
@@ -144,12 +144,16 @@ static int32_t shard_t(Ctx* c, const b2s_pk* pk, const b2s_r1cs* m, const void* 
                     (unsigned long long)m->n_instance, (unsigned long long)m->n_witness, (unsigned long long)N);
     const uint64_t n_vars = m->n_instance + m->n_witness;
     DevBuf z, h;
-    B2S_TRY(z.alloc(c, n_vars * sizeof(Fr)));
     B2S_TRY(h.alloc(c, N * sizeof(Fr)));
-    Fr* zd = z.as<Fr>();
-    B2S_CUDA(c, cudaMemcpyAsync(zd, z_inst, m->n_instance * sizeof(Fr), cudaMemcpyHostToDevice, c->stream));
-    if (m->n_witness)
-        B2S_CUDA(c, cudaMemcpyAsync(zd + m->n_instance, z_wit, m->n_witness * sizeof(Fr), cudaMemcpyHostToDevice, c->stream));
+    const Fr* zd = reinterpret_cast<const Fr*>(z_dev);
+    if (!zd) {
+        B2S_TRY(z.alloc(c, n_vars * sizeof(Fr)));
+        Fr* zw = z.as<Fr>();
+        B2S_CUDA(c, cudaMemcpyAsync(zw, z_inst, m->n_instance * sizeof(Fr), cudaMemcpyHostToDevice, c->stream));
+        if (m->n_witness)
+            B2S_CUDA(c, cudaMemcpyAsync(zw + m->n_instance, z_wit, m->n_witness * sizeof(Fr), cudaMemcpyHostToDevice, c->stream));
+        zd = zw;
+    }
     B2S_TRY(witness_map_run(c, m, zd, h.p));
     P1* g1 = reinterpret_cast<P1*>(g1_out);
     B2S_TRY(msm_run(c, 1, pk->h_query.p, h.as<Fr>() + pk->h_off, pk->h_len, true, g1 + 0));
@@ -160,9 +164,9 @@ static int32_t shard_t(Ctx* c, const b2s_pk* pk, const b2s_r1cs* m, const void* 
     return B2S_OK;
 }
 
-int32_t groth16_shard(Ctx* c, const b2s_pk* pk, const b2s_r1cs* m, const void* z_inst, const void* z_wit, void* g1_out,
-                      void* g2_out) {
-    return dispatch_curve(c, [&](auto curve) { return shard_t<decltype(curve)>(c, pk, m, z_inst, z_wit, g1_out, g2_out); });
+int32_t groth16_shard(Ctx* c, const b2s_pk* pk, const b2s_r1cs* m, const void* z_inst, const void* z_wit, const void* z_dev,
+                      void* g1_out, void* g2_out) {
+    return dispatch_curve(c, [&](auto curve) { return shard_t<decltype(curve)>(c, pk, m, z_inst, z_wit, z_dev, g1_out, g2_out); });
 }
 
 template <class Curve>

@@ -31,8 +31,9 @@ int32_t spmv_run(Ctx* c, const b2s_r1cs* m, const void* z_dev, void* out_a, void
 // h_dev: device array of domain elements (output); z_dev: n_instance + n_witness elements
 int32_t witness_map_run(Ctx* c, const b2s_r1cs* m, const void* z_dev, void* h_dev);
 int32_t pk_upload(Ctx* c, const b2s_pk_desc* d, int32_t mem, b2s_pk** out);
+// z either as two host pieces (z_dev == nullptr) or as one device array
 int32_t groth16_shard(Ctx* c, const b2s_pk* pk, const b2s_r1cs* m, const void* z_inst_host, const void* z_wit_host,
-                      void* g1_partials_dev /*4 xyzz*/, void* g2_partial_dev /*1 xyzz*/);
+                      const void* z_dev, void* g1_partials_dev /*4 xyzz*/, void* g2_partial_dev /*1 xyzz*/);
 int32_t groth16_finish(Ctx* c, const b2s_pk* pk, const void* g1_partials_dev, const void* g2_partials_dev, uint32_t n_shards,
                        const void* r_host, const void* s_host, void* out_a, void* out_b, void* out_c);
 }  // namespace b2s

@@ -62,6 +62,10 @@ SIGNATURES = {
     "b2s_pk_free": (None, [c_void_p, c_void_p]),
     "b2s_groth16_prove": (c_int32, [c_void_p] * 10),
     "b2s_groth16_prove_shard": (c_int32, [c_void_p] * 7),
+    "b2s_groth16_prove_resident": (c_int32, [c_void_p] * 9),
+    "b2s_groth16_prove_shard_resident": (c_int32, [c_void_p] * 6),
+    "b2s_profile_enable": (c_int32, [c_void_p, c_int32]),
+    "b2s_profile_report": (c_int32, [c_void_p, c_char_p, c_uint64]),
     "b2s_groth16_finish": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_uint32, c_void_p, c_void_p, c_void_p,
                                      c_void_p, c_void_p]),
     "b2s_fixed_base_g1": (c_int32, [c_void_p, c_void_p, c_uint64, c_int32, c_int32, c_void_p]),
@@ -255,6 +259,31 @@ class Backend:
         self._ck(self.lib.b2s_groth16_prove(self.h, pk, m, _ptr(z_inst)[0], _ptr(z_wit)[0], r.ctypes.data, s.ctypes.data,
                                             a.ctypes.data, b.ctypes.data, c.ctypes.data))
         return a, b, c
+
+    def groth16_prove_resident(self, pk, m, z_dev, r, s):
+        a, b, c = self._proof_bufs()
+        self._ck(self.lib.b2s_groth16_prove_resident(self.h, pk, m, _ptr(z_dev)[0], r.ctypes.data, s.ctypes.data,
+                                                     a.ctypes.data, b.ctypes.data, c.ctypes.data))
+        return a, b, c
+
+    def groth16_prove_shard_resident(self, pk, m, z_dev):
+        g1 = np.zeros(4 * self.g1x_bytes // 4, dtype=np.uint32)
+        g2 = np.zeros(self.g2x_bytes // 4, dtype=np.uint32)
+        self._ck(self.lib.b2s_groth16_prove_shard_resident(self.h, pk, m, _ptr(z_dev)[0], g1.ctypes.data, g2.ctypes.data))
+        return g1, g2
+
+    def profile(self, on=True):
+        self._ck(self.lib.b2s_profile_enable(self.h, int(on)))
+
+    def profile_report(self):
+        """{kernel name: (launches, total_ms)} since the last report."""
+        buf = ctypes.create_string_buffer(1 << 16)
+        self._ck(self.lib.b2s_profile_report(self.h, buf, len(buf)))
+        out = {}
+        for line in buf.value.decode().splitlines():
+            name, cnt, ms = line.split("\t")
+            out[name] = (int(cnt), float(ms))
+        return out
 
     def groth16_prove_shard(self, pk, m, z_inst, z_wit):
         g1 = np.zeros(4 * self.g1x_bytes // 4, dtype=np.uint32)

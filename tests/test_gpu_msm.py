@@ -102,7 +102,7 @@ def test_msm_known_discrete_logs(be, group, log_n):
     bases = torch.empty(n * pt_bytes // 4, dtype=torch.int32, device="cuda")
     be.fixed_base(group, ks_t, n, mont=False, out=bases)
     rng = np.random.default_rng(0xB2000001)
-    raw = random_fr_limbs(rng, n)
+    raw = random_fr_limbs(rng, n, bits=curve.r.bit_length() - 1)
     s_t = torch.from_numpy(raw.view(np.int32)).cuda()
     fn = be.msm_g1 if group == 1 else be.msm_g2
     got = unpack_points(curve, group, fn(bases, s_t, n, mont=True))[0]

@@ -1,0 +1,145 @@
+"""Pins the pure-Python oracle: against the reference's golden vectors where the reference has them
+(R1CS matrices / satisfiability: gr1cs/tests/{circuit1,circuit2}.rs, tests/mod.rs) and against
+implementation-independent definitions everywhere else (parity for MSM / NTT / proofs
+is otherwise unpinned because the reference tree holds none of that arithmetic)."""
+import random
+
+import pytest
+
+from oracle import groth16 as og
+from oracle import msm as omsm
+from oracle import ntt as ontt
+from oracle import r1cs as orc
+from oracle.ec import groups
+from oracle.params import BLS12_381, BN254
+
+CURVES = [BLS12_381, BN254]
+
+
+@pytest.mark.parametrize("curve", CURVES, ids=lambda c: c.name)
+def test_curve_constants(curve):
+    G1, G2 = groups(curve)
+    assert G1.on_curve(G1.gen) and G2.on_curve(G2.gen)
+    assert G1.mul(G1.gen, curve.r) is None and G2.mul(G2.gen, curve.r) is None   # generator order
+    assert G1.mul(G1.gen, curve.r - 1) == G1.neg(G1.gen)
+    S = curve.fr_two_adicity
+    assert (curve.r - 1) % (1 << S) == 0 and ((curve.r - 1) >> S) % 2 == 1      # two-adicity
+    w = curve.fr_root_of_unity
+    assert pow(w, 1 << (S - 1), curve.r) == curve.r - 1                           # exact order 2^S
+    assert pow(curve.fr_generator, (curve.r - 1) // 2, curve.r) == curve.r - 1   # generator is a non-residue
+    if curve is BLS12_381:  # SURVEY Appendix B value
+        assert w == 0x16A2A19EDFE81F20D09B681922C813B4B63683508C2280B93829971F439F0D2B
+
+
+def test_reference_golden_circuit2():
+    """test_circuit2_matrices (gr1cs/tests/mod.rs:136-147): matrices after finalize == circuit2.rs:21-43."""
+    cs = orc.circuit2(BLS12_381, 1, 1, 2)
+    cs.finalize()
+    assert cs.to_matrices() == orc.CIRCUIT2_GOLDEN
+    assert cs.is_satisfied()
+    z = cs.z()
+    A, B, C = cs.to_matrices()
+    r = BLS12_381.r
+    az, bz, cz = (orc.mat_vec_mul(r, M, z) for M in (A, B, C))
+    assert (az, bz, cz) == ([1, 1, 1], [2, 2, 4], [2, 2, 4])                      # 1*2=2, 1*2=2, 1*4=4
+    assert [orc.evaluate_constraint(r, row, z) for row in B] == bz
+    # a wrong witness is rejected
+    bad = orc.circuit2(BLS12_381, 1, 1, 3)
+    assert bad.which_is_unsatisfied() == ("R1CS", 0)
+
+
+def test_reference_golden_circuit1():
+    """test_circuit1_matrices / _sat / _non_sat (gr1cs/tests/mod.rs:17-103)."""
+    cs = orc.circuit1(BLS12_381, (0,) * 5, (0,) * 8)
+    assert cs.to_matrices_all() == orc.CIRCUIT1_GOLDEN          # before finalize, as the reference asserts
+    sat = orc.circuit1(BLS12_381, *orc.CIRCUIT1_SAT)
+    sat.finalize()
+    assert sat.is_satisfied()
+    assert not orc.circuit1(BLS12_381, *orc.CIRCUIT1_UNSAT).is_satisfied()
+
+
+def test_dummy_circuit_shapes():
+    """DummyCircuit (sr1cs/mod.rs:296-317): builder output == the direct generator used at scale."""
+    for curve in CURVES:
+        cs = orc.dummy_circuit(curve, 3, 5, 16, 16)
+        mats, inst, wit = orc.dummy_circuit_direct(curve, 3, 5, 16, 16)
+        assert cs.to_matrices() == mats and cs.instance_assignment == inst and cs.witness_assignment == wit
+        assert cs.is_satisfied() and cs.num_instance_variables == 2 and cs.num_witness_variables == 15
+        assert mats[0][-1] == [] and mats[1][-1] == [] and mats[2][-1] == []
+
+
+def test_lc_quirks():
+    """`lc + var` on a short LC inserts a duplicate; compactify merges on inlining."""
+    r = BLS12_381.r
+    v = orc.witness(0)
+    l = orc.LinearCombination(r) + v + v
+    assert l.t == [(1, v), (1, v)]
+    l.compactify()
+    assert l.t == [(2, v)]
+    assert orc.variable_index(orc.V_ONE, 5) == 0 and orc.variable_index(orc.instance(3), 5) == 3
+    assert orc.variable_index(orc.witness(2), 5) == 7 and orc.variable_index(orc.symbolic_lc(1), 5) is None
+    assert sorted([orc.symbolic_lc(0), orc.witness(9), orc.instance(1), orc.V_ONE, orc.V_ZERO]) == [
+        orc.V_ZERO, orc.V_ONE, orc.instance(1), orc.witness(9), orc.symbolic_lc(0)]  # variable.rs:206-266
+
+
+@pytest.mark.parametrize("curve", CURVES, ids=lambda c: c.name)
+def test_ntt_against_definition(curve):
+    rng = random.Random(1)
+    for log_n in range(0, 8):
+        x = [rng.randrange(curve.r) for _ in range(1 << log_n)]
+        assert ontt.ntt(curve, x) == ontt.dft_naive(curve, x)
+        assert ontt.ntt(curve, x, inverse=True) == ontt.dft_naive(curve, x, inverse=True)
+        assert ontt.ntt(curve, ontt.ntt(curve, x), inverse=True) == x
+        assert ontt.coset_intt(curve, ontt.coset_ntt(curve, x)) == x
+        g, w = curve.fr_generator, curve.omega(log_n)
+        direct = [sum(x[j] * pow(g * pow(w, i, curve.r), j, curve.r) for j in range(len(x))) % curve.r for i in range(len(x))]
+        assert ontt.coset_ntt(curve, x) == direct
+
+
+@pytest.mark.parametrize("curve,group", [(BLS12_381, 1), (BLS12_381, 2), (BN254, 1), (BN254, 2)], ids=str)
+def test_msm_against_definition(curve, group):
+    G = groups(curve)[group - 1]
+    rng = random.Random(2)
+    bases = [G.mul(G.gen, rng.randrange(1, curve.r)) for _ in range(40)]
+    s = [rng.randrange(curve.r) for _ in range(40)]
+    t = [rng.randrange(curve.r) for _ in range(40)]
+    assert omsm.msm_pippenger(G, bases, s) == omsm.msm_naive(G, bases, s)
+    lhs = omsm.msm_pippenger(G, bases, [(a + b) % curve.r for a, b in zip(s, t)])
+    assert lhs == G.add(omsm.msm_pippenger(G, bases, s), omsm.msm_pippenger(G, bases, t))   # linearity
+    assert omsm.msm_pippenger(G, bases[:1], [0]) is None
+
+
+def test_window_rule_and_add_counts():
+    """SURVEY App. A.4 / 8d figures."""
+    assert [omsm.ark_window_bits(1 << k) for k in (16, 20, 22, 24, 26)] == [13, 15, 17, 18, 19]
+    assert omsm.ark_window_bits(31) == 3
+    assert omsm.reference_add_count(1 << 22, 255) == (1 << 22) * 15 + 15 * (1 << 17) == 64880640
+    assert abs(omsm.reference_add_count(1 << 24, 255) - 2.56e8) < 0.01e8
+    assert abs(omsm.reference_add_count(1 << 26, 255) - 9.47e8) < 0.01e8
+    for k in (0, 1, (1 << 255) - 19, BLS12_381.r - 1):
+        for c in (3, 13, 16, 17):
+            d = omsm.signed_digits(k, c, 255)
+            assert sum(v << (c * i) for i, v in enumerate(d)) == k
+
+
+@pytest.mark.parametrize("curve", CURVES, ids=lambda c: c.name)
+def test_groth16_known_trapdoor(curve):
+    rng = random.Random(0xB2000003)
+    for cs in (orc.circuit2(curve, 1, 1, 2), orc.dummy_circuit(curve, 3, 5, 8, 8), orc.bench_circuit(curve, 6, seed=1)):
+        cs.finalize()
+        assert cs.is_satisfied()
+        mats, inst, wit = cs.to_matrices(), cs.instance_assignment, cs.witness_assignment
+        td = og.Trapdoor(*[rng.randrange(1, curve.r) for _ in range(5)])
+        pk = og.setup(curve, mats, len(inst), len(wit), td)
+        rr, ss = rng.randrange(curve.r), rng.randrange(curve.r)
+        A, B, C, h = og.prove(pk, mats, inst, wit, rr, ss)
+        assert h[-1] == 0                                           # deg h <= N - 2
+        assert og.check_in_exponent(pk, (A, B, C), inst, wit, h, rr, ss)
+        exps = og.expected_proof_exponents(pk, inst, wit, h, rr, ss)
+        assert og.verify_equation_in_exponent(pk, inst, *exps)     # e(A,B) = e(alpha,beta) e(IC,gamma) e(C,delta)
+        # an unsatisfying witness does not verify
+        bad = list(wit)
+        bad[0] = (bad[0] + 1) % curve.r
+        _, _, _, hb = og.prove(pk, mats, inst, bad, rr, ss)
+        eb = og.expected_proof_exponents(pk, inst, bad, hb, rr, ss)
+        assert not og.verify_equation_in_exponent(pk, inst, *eb)
