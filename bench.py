@@ -1,0 +1,458 @@
+#!/usr/bin/env python
+"""bench.py -- Groth16 prove() on a synthetic DummyCircuit-shaped R1CS (BLS12-381), the hot path that
+BASELINE.json's metric is quoted on, through libb200snark.so on 1..8 B200s; plus the CPU reference arm.
+
+  python bench.py --gpus N --steps K --warmup W            (torchrun for N > 1, one rank per GPU)
+  python bench.py --impl reference ...                     (CPU restatement of the reference algorithms)
+
+One "step" = one proof: R1CS matrices x witness (SpMV) -> 7 NTTs -> 4 G1 MSMs + 1 G2 MSM -> epilogue.
+`value` times proofs with z already resident in HBM; `e2e` times the public C-ABI call with z in pinned
+host memory (H2D inside) and the proof read back to the host.  N > 1: strong scaling -- the five MSMs
+are cut by base range over the ranks (each rank holds 1/N of the proving key), partial sums are
+all-gathered with NCCL and rank 0 applies the epilogue.  See DESIGN.md for the roofline accounting.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+BLS_R = 0x73EDA753299D7D483339D80809A1D80553BDA402FFFE5BFEFFFFFFFF00000001
+R256 = 1 << 256
+SEED_PK, SEED_RS, SEED_Z = 0xB2000003, 0xB2000004, 0xB2000005
+
+
+def limbs(x):
+    return np.array([(x >> (32 * i)) & 0xFFFFFFFF for i in range(8)], dtype=np.uint32)
+
+
+def mont(x):
+    return limbs(x * R256 % BLS_R)
+
+
+def ark_window_bits(n):
+    if n < 32:
+        return 3
+    return (n - 1).bit_length() * 69 // 100 + 2
+
+
+def msm_window_choice(n, point_bytes, bits=255):
+    """(c, windows) the library picks for an n-point MSM (same cost model as msm_shape in csrc/msm.cu)."""
+    best, best_c = None, 5
+    for c in range(5, 21):
+        nw = -(-bits // c)
+        if bits - (nw - 1) * c >= c:
+            nw += 1
+        buckets = nw * (1 << (c - 1))
+        if buckets * point_bytes > 4 << 30:
+            break
+        cost = n * nw + buckets * 4.7
+        if best is None or cost < best:
+            best, best_c, best_nw = cost, c, nw
+    return best_c, best_nw
+
+
+def reference_add_count(n, bits=255):
+    """G1 additions ark-ec's Pippenger performs for an n-point MSM: N*ceil(l/c) + ceil(l/c)*2^c."""
+    c = ark_window_bits(n)
+    w = -(-bits // c)
+    return n * w + w * (1 << c)
+
+
+# ------------------------------------------------------------------------------------------------
+# synthetic instance (shared by both arms): DummyCircuit shape (relations/src/sr1cs/mod.rs:296-317)
+# emitted directly as CSR, with n_rows + n_instance == 2^log_n so the QAP domain is exactly 2^log_n.
+# ------------------------------------------------------------------------------------------------
+def dummy_instance(log_n):
+    N = 1 << log_n
+    n_rows, n_inst = N - 2, 2
+    n_wit = N - 3                      # a, b and N-5 copies of a  (n_vars = N - 1, h_query has N - 1 points)
+    one = mont(1)
+    nnz = n_rows - 1                   # the last constraint is empty (lc![] * lc![] = lc![])
+    row_ptr = np.minimum(np.arange(n_rows + 1, dtype=np.uint64), np.uint64(nnz))
+    coeff = np.tile(one, nnz)
+    csr = [(row_ptr, np.full(nnz, col, dtype=np.uint32), coeff) for col in (2, 3, 1)]   # A: a, B: b, C: c = a*b
+    rng = np.random.default_rng(SEED_Z)
+    a = int.from_bytes(rng.bytes(32), "little") % BLS_R
+    b = int.from_bytes(rng.bytes(32), "little") % BLS_R
+    z_inst = np.concatenate([one, mont(a * b % BLS_R)])
+    z_wit = np.tile(mont(a), n_wit)
+    z_wit[8:16] = mont(b)
+    return dict(N=N, n_rows=n_rows, n_inst=n_inst, n_wit=n_wit, csr=csr, z_inst=z_inst, z_wit=z_wit)
+
+
+def rs_scalars():
+    rng = np.random.default_rng(SEED_RS)
+    r = int.from_bytes(rng.bytes(32), "little") % BLS_R
+    s = int.from_bytes(rng.bytes(32), "little") % BLS_R
+    return mont(r), mont(s)
+
+
+def shard_range(total, rank, world):
+    return total * rank // world, total * (rank + 1) // world
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.device, self.proc, self.lines = device, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+                                          "-i", str(self.device)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        sm, reasons, mx = [], set(), None
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx = float(f[1])
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def hbm_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured"
+    except Exception:
+        return 6650.0, "fallback"
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm: the C++ restatement of ark-ec / ark-poly / ark-groth16 (oracle/c/oracle.cpp) on all host cores
+# ------------------------------------------------------------------------------------------------
+def cpu_prove_sample(log_n_sample, steps, warmup, threads=None):
+    from oracle import cnative   # the one place outside tests/ that executes oracle/: the CPU baseline
+
+    threads = threads or cnative.threads_default()
+    inst = dummy_instance(log_n_sample)
+    N, n_vars = inst["N"], inst["n_inst"] + inst["n_wit"]
+    # synthetic key: multiples of the generators (distinct valid points; structure does not affect timing)
+    g1 = np.array(_G1_GEN_MONT, dtype=np.uint32)
+    g2 = np.array(_G2_GEN_MONT, dtype=np.uint32)
+    mk1 = lambda start, n: cnative.multiples(0, 1, g1, start, n, threads)
+    mk2 = lambda start, n: cnative.multiples(0, 2, g2, start, n, threads)
+    pk = [mk1(3, 1), mk1(5, 1), mk1(7, 1), mk2(5, 1), mk2(7, 1), mk1(11, n_vars), mk1(11 + N, n_vars), mk2(13, n_vars),
+          mk1(11 + 2 * N, N - 1), mk1(11 + 3 * N, inst["n_wit"])]
+    r, s = rs_scalars()
+    times = []
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        cnative.groth16_prove(0, inst["csr"], inst["n_rows"], inst["n_inst"], inst["n_wit"], pk, inst["z_inst"], inst["z_wit"], r, s,
+                              threads=threads)
+        dt = time.perf_counter() - t0
+        if it >= warmup:
+            times.append(dt)
+    return float(np.mean(times)), threads
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return  # rank 0 alone runs the CPU arm
+    cores = os.cpu_count() or 1
+    log_s = args.ref_log_n or (20 if cores >= 64 else 16)
+    log_s = min(log_s, args.log_n)
+    sec, threads = cpu_prove_sample(log_s, args.steps, args.warmup)
+    scale = (1 << log_s) / (1 << args.log_n)          # work is ~linear in the domain size (MSM-dominated)
+    value = scale / sec
+    sample = (f"Groth16 prove of the same DummyCircuit-shaped R1CS at domain 2^{log_s} ({sec:.3f} s/proof on {threads} threads), "
+              f"scaled linearly to 2^{args.log_n}")
+    out = {
+        "impl": "reference", "metric": "groth16_proofs_per_sec", "value": value, "unit": "proofs/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 / value, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "u32 limbs (255/381-bit modular integers)", "data": "synthetic",
+        "config": workload_config(args, 1),
+        "cpu_baseline": {"value": value, "unit": "proofs/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "proofs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "note": "C++ restatement of the ark-ec/ark-poly/ark-groth16 algorithms (no Rust toolchain here); MSMs are chunked over "
+                "all host threads, which is stronger than ark-ec's per-window rayon parallelism",
+    }
+    print(json.dumps(out), flush=True)
+
+
+def workload_config(args, world):
+    return {"workload": f"Groth16 prove, BLS12-381, DummyCircuit-shaped R1CS, QAP domain 2^{args.log_n} "
+                        f"({(1 << args.log_n) - 2} constraints, {(1 << args.log_n) - 1} variables)",
+            "log_domain": args.log_n, "curve": "bls12_381", "parallelism": f"msm base-range shard x{world}",
+            "l2": "inputs larger than L2 (proving key 9 GiB at 2^24); no flush needed"}
+
+
+# ------------------------------------------------------------------------------------------------
+# B200 arm
+# ------------------------------------------------------------------------------------------------
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+
+    import snark_b200
+    from snark_b200 import shard
+    from snark_b200.lib import MEM_DEVICE, PkDesc
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    be = snark_b200.Backend(curve=0, device=local)   # raises (no fallback) without the .so or a B200
+    ext = torch.cuda.ExternalStream(be.stream, device=dev)
+
+    inst = dummy_instance(args.log_n)
+    N, n_inst, n_wit = inst["N"], inst["n_inst"], inst["n_wit"]
+    n_vars = n_inst + n_wit
+    mat = be.r1cs_upload(inst["n_rows"], n_inst, n_wit, inst["csr"])
+    inst["csr"] = None
+
+    # --- synthetic proving key with known discrete logs, built on the GPU by the fixed-base kernel ----
+    def rand_scalars(n, seed):
+        g = torch.Generator(device=dev)
+        g.manual_seed(seed)
+        t = torch.randint(-(1 << 31), (1 << 31) - 1, (n, 8), dtype=torch.int32, device=dev, generator=g)
+        t[:, 7] &= 0x1FFFFFFF           # < 2^253 < r: canonical scalars
+        return t
+
+    def make_query(group, total, seed):
+        lo, hi = shard_range(total, rank, world)
+        k = rand_scalars(hi - lo, seed * 1000 + rank)
+        out = torch.empty(((hi - lo) * (be.g1_bytes if group == 1 else be.g2_bytes)) // 4, dtype=torch.int32, device=dev)
+        be.fixed_base(group, k, hi - lo, mont=False, out=out)
+        be.sync()
+        return out, lo, hi - lo
+
+    consts1 = torch.empty(3 * be.g1_bytes // 4, dtype=torch.int32, device=dev)
+    consts2 = torch.empty(2 * be.g2_bytes // 4, dtype=torch.int32, device=dev)
+    be.fixed_base(1, rand_scalars(3, SEED_PK), 3, mont=False, out=consts1)
+    be.fixed_base(2, rand_scalars(2, SEED_PK + 1), 2, mont=False, out=consts2)
+    d = PkDesc()
+    d.n_instance, d.n_witness, d.domain_size = n_inst, n_wit, N
+    g1w, g2w = be.g1_bytes, be.g2_bytes
+    d.alpha_g1, d.beta_g1, d.delta_g1 = consts1.data_ptr(), consts1.data_ptr() + g1w, consts1.data_ptr() + 2 * g1w
+    d.beta_g2, d.delta_g2 = consts2.data_ptr(), consts2.data_ptr() + g2w
+    keep = []
+    for name, off, ln, group, total, seed in (("a_query", "a_off", "a_len", 1, n_vars, 11), ("b_g1_query", "b1_off", "b1_len", 1, n_vars, 12),
+                                              ("b_g2_query", "b2_off", "b2_len", 2, n_vars, 13), ("h_query", "h_off", "h_len", 1, N - 1, 14),
+                                              ("l_query", "l_off", "l_len", 1, n_wit, 15)):
+        t, lo, cnt = make_query(group, total, SEED_PK + seed)
+        keep.append(t)
+        setattr(d, name, t.data_ptr()); setattr(d, off, lo); setattr(d, ln, cnt)
+    pk = be.pk_upload(d, mem=MEM_DEVICE)
+    keep.clear()
+    torch.cuda.empty_cache()
+
+    r, s = rs_scalars()
+    z_host = torch.from_numpy(np.concatenate([inst["z_inst"], inst["z_wit"]]).view(np.int32)).pin_memory()
+    z_dev = z_host.to(dev)
+    gather_words = (4 * be.g1x_bytes + be.g2x_bytes) // 4
+
+    def prove(resident):
+        """One proof; returns the proof (rank 0) -- every rank takes part."""
+        if world == 1:
+            if resident:
+                return be.groth16_prove_resident(pk, mat, z_dev, r, s)
+            return be.groth16_prove(pk, mat, zi_ptr_obj, zw_ptr_obj, r, s)
+        if resident:
+            shard_fn = lambda: be.groth16_prove_shard_resident(pk, mat, z_dev)
+        else:
+            shard_fn = lambda: be.groth16_prove_shard(pk, mat, zi_ptr_obj, zw_ptr_obj)
+        # the one exchange of the path: an NCCL all-gather of 5 partial points per rank, joined on rank 0
+        return shard.sharded_prove(dist, rank, world, shard_fn, lambda p1, p2, w: be.groth16_finish(pk, p1, p2, w, r, s),
+                                   be.g1x_bytes // 4, be.g2x_bytes // 4, device=dev)
+
+    # views of the pinned host buffer (Backend passes their addresses through as HOST memory)
+    zi_ptr_obj = z_host[: n_inst * 8].numpy()
+    zw_ptr_obj = z_host[n_inst * 8:].numpy()
+
+    def timed(resident, steps, warmup, profile=False):
+        for _ in range(warmup):
+            prove(resident)
+        be.sync(); torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        if profile:
+            be.profile(True)
+        launches0 = be.launches
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(ext)
+        t0 = time.perf_counter()
+        proof = None
+        for _ in range(steps):
+            proof = prove(resident)
+        e1.record(ext)
+        be.sync(); torch.cuda.synchronize()
+        wall = time.perf_counter() - t0
+        if world > 1:
+            dist.barrier()
+        ms = torch.tensor([e0.elapsed_time(e1), wall * 1e3], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        rep = be.profile_report() if profile else None
+        if profile:
+            be.profile(False)
+        return float(ms[0]), float(ms[1]), be.launches - launches0, rep, proof
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    dev_ms, wall_ms, launches, rep, proof_a = timed(True, args.steps, args.warmup, profile=True)
+    clocks = sampler.stop() if rank == 0 else None
+    e2e_ms, e2e_wall, _, _, proof_b = timed(False, args.steps, 1)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    assert all(np.array_equal(x, y) for x, y in zip(proof_a, proof_b)), "resident and host-buffer proofs differ"
+    value = args.steps / (dev_ms / 1e3)
+    e2e_value = args.steps / (e2e_ms / 1e3)
+
+    # ---- roofline of the dominant kernel (CUDA events around every launch in the timed region) -------
+    peak, peak_src = hbm_peak()
+    kern, (cnt, tot_ms) = max(rep.items(), key=lambda kv: kv[1][1])
+    share = tot_ms / sum(v[1] for v in rep.values())
+    pts_per_launch = {"msm_accumulate_g1": (N - 1) / world, "msm_accumulate_g2": (N - 1) / world}.get(kern)
+    bytes_per_pt = {"msm_accumulate_g1": 128, "msm_accumulate_g2": 224}.get(kern)
+    roof = {"kernel": kern, "bound": "hbm", "unit": "GB/s", "peak": peak, "peak_source": peak_src, "traffic": None,
+            "launches": cnt, "avg_launch_ms": tot_ms / cnt, "share_of_step": share}
+    if pts_per_launch:
+        alg = pts_per_launch * bytes_per_pt
+        ach = alg / (tot_ms / cnt * 1e-3) / 1e9
+        roof.update({"achieved": ach, "frac": ach / peak, "algorithmic_bytes_per_launch": alg})
+        # honest companion: the kernel is fma-pipe bound; additions/s against the measured ceiling of
+        # tools/microbench.cu (2.9e9 mixed G1 additions/s on this part, profiles/r01_microbench.txt)
+        c_bits, nwin = msm_window_choice(int(pts_per_launch), 192 if kern.endswith("g1") else 384)
+        adds = pts_per_launch * nwin / (tot_ms / cnt * 1e-3)
+        ceil_ = 2.9e9 if kern.endswith("g1") else None
+        roof["alu"] = {"unit": f"bucket additions/s (c={c_bits}, {nwin} windows)", "achieved": adds, "peak": ceil_,
+                       "frac": adds / ceil_ if ceil_ else None,
+                       "note": "peak = mixed G1 additions/s of tools/microbench.cu (fmaheavy-pipe bound); ncu shows "
+                               "sm__pipe_fmaheavy_cycles_active ~86% for this kernel (profiles/)"}
+    msm_adds = 4 * reference_add_count(N) * value   # four ~N-point G1 MSMs per proof, reference add count
+    out = {
+        "metric": "groth16_proofs_per_sec", "value": value, "unit": "proofs/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "u32 limbs (255/381-bit modular integers)", "data": "synthetic",
+        "config": workload_config(args, world),
+        "e2e": {"value": e2e_value, "unit": "proofs/s", "h2d_bytes_per_step": int(n_vars * 32 + 64), "d2h_bytes_per_step": int(2 * g1w + g2w),
+                "ms_per_step": e2e_ms / args.steps},
+        "gpu_launches": launches, "clocks": clocks, "roofline": roof,
+        "kernel_ms_per_step": {k: round(v[1] / args.steps, 4) for k, v in sorted(rep.items(), key=lambda kv: -kv[1][1])},
+        "msm_g1_adds_per_sec_in_prove": msm_adds, "wall_ms_per_step": wall_ms / args.steps,
+    }
+    if world == 1 and not args.no_extras:
+        out["extras"] = extras(be, torch, dev, ext, peak)
+    if world == 1 and not args.no_cpu:
+        cores = os.cpu_count() or 1
+        log_s = min(args.ref_log_n or (20 if cores >= 64 else 16), args.log_n)
+        sec, threads = cpu_prove_sample(log_s, 1, 0)
+        scale = (1 << log_s) / (1 << args.log_n)
+        out["cpu_baseline"] = {"value": scale / sec, "unit": "proofs/s", "cores": threads, "kind": "port",
+                               "sample": f"one Groth16 prove at domain 2^{log_s} ({sec:.3f} s on {threads} threads), scaled linearly to 2^{args.log_n}"}
+    print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def extras(be, torch, dev, ext, peak):
+    """BASELINE configs 2 and 3 on one GPU: 2^22-point G1 MSM and 2^24-element NTT round trip."""
+    res = {}
+
+    def time_fn(fn, reps=3):
+        fn(); be.sync()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(ext)
+        for _ in range(reps):
+            fn()
+        e1.record(ext)
+        be.sync()
+        return e0.elapsed_time(e1) / reps
+
+    g = torch.Generator(device=dev); g.manual_seed(0xB2000001)
+    n = 1 << 22
+    k = torch.randint(-(1 << 31), (1 << 31) - 1, (n, 8), dtype=torch.int32, device=dev, generator=g)
+    k[:, 7] &= 0x1FFFFFFF
+    bases = torch.empty(n * be.g1_bytes // 4, dtype=torch.int32, device=dev)
+    be.fixed_base(1, k, n, mont=False, out=bases)
+    sc = torch.randint(-(1 << 31), (1 << 31) - 1, (n, 8), dtype=torch.int32, device=dev, generator=g)
+    sc[:, 7] &= 0x1FFFFFFF
+    ms = time_fn(lambda: be.msm_g1(bases, sc, n, mont=True))
+    res["msm_g1_2p22_uniform"] = {"ms": ms, "g1_adds_per_sec_reference_count": reference_add_count(n) / (ms / 1e3),
+                                  "hbm_GBps_algorithmic": n * 128 / (ms / 1e3) / 1e9, "hbm_frac": n * 128 / (ms / 1e3) / 1e9 / peak}
+    same = sc[:1].repeat(n, 1).contiguous()
+    ms = time_fn(lambda: be.msm_g1(bases, same, n, mont=True))
+    res["msm_g1_2p22_all_equal_scalars"] = {"ms": ms, "g1_adds_per_sec_reference_count": reference_add_count(n) / (ms / 1e3)}
+    del bases, k, sc, same
+    n = 1 << 24
+    x = torch.randint(-(1 << 31), (1 << 31) - 1, (n, 8), dtype=torch.int32, device=dev, generator=g)
+    x[:, 7] &= 0x1FFFFFFF
+    ms = time_fn(lambda: be.ntt(x, 24))
+    res["ntt_2p24_forward"] = {"ms": ms, "elements_per_sec": n / (ms / 1e3), "hbm_GBps_algorithmic": n * 64 / (ms / 1e3) / 1e9,
+                               "hbm_frac": n * 64 / (ms / 1e3) / 1e9 / peak}
+    return res
+
+
+# standard generators in Montgomery limbs (the same constants as snark_b200/csrc/field_params.h)
+def _gen_limbs():
+    p = 0x1A0111EA397FE69A4B1BA7B6434BACD764774B84F38512BF6730D2A0F6B0F6241EABFFFEB153FFFFB9FEFFFFFFFFAAAB
+    R = 1 << 384
+    g1 = (0x17F1D3A73197D7942695638C4FA9AC0FC3688C4F9774B905A14E3A3F171BAC586C55E83FF97A1AEFFB3AF00ADB22C6BB,
+          0x08B3F481E3AAA0F1A09E30ED741D8AE4FCF5E095D5D00AF600DB18CB2C04B3EDD03CC744A2888AE40CAA232946C5E7E1)
+    g2 = (0x024AA2B2F08F0A91260805272DC51051C6E47AD4FA403B02B4510B647AE3D1770BAC0326A805BBEFD48056C8C121BDB8,
+          0x13E02B6052719F607DACD3A088274F65596BD0D09920B61AB5DA61BBDC7F5049334CF11213945D57E5AC7D055D042B7E,
+          0x0CE5D527727D6E118CC9CDC6DA2E351AADFD9BAA8CBDD3A76D429A695160D12C923AC9CC3BACA289E193548608B82801,
+          0x0606C4A02EA734CC32ACD2B02BC28B99CB3E287E85A763AF267492AB572E99AB3F370D275CEC1DA1AAA9075FF05F79BE)
+    f = lambda v: [((v * R % p) >> (32 * i)) & 0xFFFFFFFF for i in range(12)]
+    return sum((f(v) for v in g1), []), sum((f(v) for v in g2), [])
+
+
+_G1_GEN_MONT, _G2_GEN_MONT = _gen_limbs()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--log-n", type=int, default=24, help="log2 of the QAP domain (24 = BASELINE's headline size)")
+    ap.add_argument("--ref-log-n", type=int, default=0, help="domain of the bounded CPU sample (default: 20 with >= 64 cores, else 16)")
+    ap.add_argument("--no-extras", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

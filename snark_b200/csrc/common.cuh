@@ -60,9 +60,10 @@ inline int32_t fail(Ctx* c, int32_t code, const char* fmt, ...) {
     } while (0)
 
 // Launch + count + check.  Usage: B2S_LAUNCH(ctx, kernel<T>, grid, block, smem, args...)
-#define B2S_LAUNCH(ctx, kern, grid, block, smem, ...)                                   \
+#define B2S_LAUNCH(ctx, kern, grid, block, smem, ...) B2S_LAUNCH_N(ctx, #kern, kern, grid, block, smem, __VA_ARGS__)
+#define B2S_LAUNCH_N(ctx, label, kern, grid, block, smem, ...)                          \
     do {                                                                                \
-        ::b2s::Ctx::ProfRec pr__{#kern, nullptr, nullptr};                              \
+        ::b2s::Ctx::ProfRec pr__{label, nullptr, nullptr};                              \
         if ((ctx)->profiling) {                                                         \
             cudaEventCreate(&pr__.e0);                                                  \
             cudaEventCreate(&pr__.e1);                                                  \

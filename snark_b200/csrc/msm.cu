@@ -8,7 +8,7 @@
 // Pipeline (all on the ctx stream, no host synchronisation inside):
 //   1 count     one thread per scalar: Montgomery -> canonical, signed digits, histogram of
 //               (window, |digit|) bucket sizes (global atomics, 4 B each)
-//   2 scan      exclusive prefix sums: bucket offsets in the sorted index array, and task offsets
+//   2 scan      exclusive prefix sums (tile sums, spine, apply): bucket offsets in the sorted index array, and task offsets
 //               (a bucket of s points is cut into ceil(s / L) tasks so that no thread ever owns more
 //               than L points -- this is what keeps degenerate scalar distributions, e.g. the all-equal
 //               witness of the reference's DummyCircuit (relations/src/sr1cs/mod.rs:306-309), balanced)
@@ -18,7 +18,7 @@
 //   5 reduce    buckets that were split: one CTA sums the task partials of a bucket (shared-memory tree)
 //   6 bucket sum per window sum_b b*B_b by segments: running sums over 16 buckets per thread, then
 //               seg_start * (segment total) by double-and-add; one CTA per window adds the segments
-//   7 horner    sum_w 2^(c w) S_w, one thread (255 doublings)
+//   7 horner    sum_w 2^(c w) S_w, one thread (255 doublings; multiplication inlined for ILP, msm_acc_g*.cu)
 //
 // Roofline: per (point, scalar) the algorithmic HBM traffic is 96+32 B (G1 BLS12-381), but each point
 // costs ceil(255/c) mixed additions of ~10 Fq multiplications = ~3000 wide IMADs; the kernel is
@@ -58,55 +58,131 @@ __device__ __forceinline__ void load_scalar(DigitIter& it, const Fr* scalars, ui
     it.carry = 0;
 }
 
+// Histogram of (window, |digit|).  Lanes of a warp that hit the same bucket are combined with
+// match.any so that skewed scalar distributions (all-equal witnesses, many 0/1 values) issue one
+// atomic per distinct bucket per warp instead of 32 to the same address.
 template <class Fr>
 __global__ void msm_count_kernel(const Fr* __restrict__ scalars, uint64_t n, bool mont, MsmShape sh,
                                  uint32_t* __restrict__ counts) {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
+    const unsigned active = __activemask();
+    const unsigned lane = threadIdx.x & 31;
     DigitIter it;
     load_scalar(it, scalars, i, mont);
     for (uint32_t w = 0; w < sh.nwin; w++) {
         const int32_t d = it.next(w, sh.c, sh.nwin);
-        if (d != 0) atomicAdd(&counts[w * sh.B + (uint32_t)(d < 0 ? -d : d) - 1], 1u);
+        const uint32_t key = d != 0 ? w * sh.B + (uint32_t)(d < 0 ? -d : d) - 1 : 0xffffffffu;
+        const unsigned peers = __match_any_sync(active, key);
+        if (key != 0xffffffffu && lane == (unsigned)(__ffs(peers) - 1)) atomicAdd(&counts[key], (uint32_t)__popc(peers));
     }
 }
 
-// Single-CTA exclusive scans over G entries: offsets[g] (points) and task_off[g] (tasks); also
-// appends split buckets to `heavy` (list) with heavy[0] = count.
-__global__ void msm_scan_kernel(const uint32_t* __restrict__ counts, MsmShape sh, uint32_t* __restrict__ offsets,
-                                uint32_t* __restrict__ task_off, uint32_t* __restrict__ heavy) {
-    __shared__ uint32_t s_pts[1024], s_tsk[1024], s_hvy[1024];
-    const uint32_t tid = threadIdx.x, nt = blockDim.x;
-    const uint32_t per = (sh.G + nt - 1) / nt;
-    const uint32_t lo = min(tid * per, sh.G), hi = min(lo + per, sh.G);
-    uint32_t pts = 0, tsk = 0, hvy = 0;
-    for (uint32_t g = lo; g < hi; g++) {
-        const uint32_t s = counts[g];
-        const uint32_t t = (s + sh.L - 1) / sh.L;
-        pts += s; tsk += t; hvy += (t > 1);
+// Exclusive scans over the G bucket counts, in three kernels (tile sums -> scan of tile sums -> apply):
+//   offsets[g]  = number of points in buckets < g        (position in the sorted index array)
+//   task_off[g] = number of tasks in buckets < g         (a bucket of s points has ceil(s / L) tasks)
+//   heavy[1..]  = buckets that were split (more than one task), heavy[0] = how many
+static constexpr int SCAN_THREADS = 256;
+static constexpr int SCAN_PER_THREAD = 8;
+static constexpr int SCAN_TILE = SCAN_THREADS * SCAN_PER_THREAD;
+
+struct Scan3 { uint32_t pts, tsk, hvy; };
+__device__ __forceinline__ Scan3 operator+(const Scan3& a, const Scan3& b) { return {a.pts + b.pts, a.tsk + b.tsk, a.hvy + b.hvy}; }
+
+// inclusive block scan of one Scan3 per thread; returns the inclusive prefix, total in *total
+__device__ __forceinline__ Scan3 block_scan(Scan3 v, Scan3* total) {
+    __shared__ Scan3 warp_tot[32];
+    const unsigned lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        Scan3 o = {__shfl_up_sync(0xffffffffu, v.pts, d), __shfl_up_sync(0xffffffffu, v.tsk, d), __shfl_up_sync(0xffffffffu, v.hvy, d)};
+        if (lane >= (unsigned)d) v = v + o;
     }
-    s_pts[tid] = pts; s_tsk[tid] = tsk; s_hvy[tid] = hvy;
+    if (lane == 31) warp_tot[wid] = v;
     __syncthreads();
-    // Hillis-Steele inclusive scan over the per-thread totals
-    for (uint32_t d = 1; d < nt; d <<= 1) {
-        uint32_t a = 0, b = 0, h = 0;
-        if (tid >= d) { a = s_pts[tid - d]; b = s_tsk[tid - d]; h = s_hvy[tid - d]; }
-        __syncthreads();
-        s_pts[tid] += a; s_tsk[tid] += b; s_hvy[tid] += h;
-        __syncthreads();
+    const unsigned nw = (blockDim.x + 31) >> 5;
+    if (wid == 0) {
+        Scan3 w = lane < nw ? warp_tot[lane] : Scan3{0, 0, 0};
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            Scan3 o = {__shfl_up_sync(0xffffffffu, w.pts, d), __shfl_up_sync(0xffffffffu, w.tsk, d), __shfl_up_sync(0xffffffffu, w.hvy, d)};
+            if (lane >= (unsigned)d) w = w + o;
+        }
+        warp_tot[lane] = w;
     }
-    uint32_t bp = s_pts[tid] - pts, bt = s_tsk[tid] - tsk, bh = s_hvy[tid] - hvy;
-    for (uint32_t g = lo; g < hi; g++) {
-        const uint32_t s = counts[g];
-        const uint32_t t = (s + sh.L - 1) / sh.L;
-        offsets[g] = bp; task_off[g] = bt;
-        if (t > 1) heavy[1 + bh++] = g;
-        bp += s; bt += t;
+    __syncthreads();
+    if (wid > 0) v = v + warp_tot[wid - 1];
+    *total = warp_tot[nw - 1];
+    __syncthreads();
+    return v;
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS)
+msm_scan_tiles_kernel(const uint32_t* __restrict__ counts, MsmShape sh, Scan3* __restrict__ tile_sums) {
+    const uint32_t base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_PER_THREAD;
+    Scan3 v{0, 0, 0};
+#pragma unroll
+    for (int k = 0; k < SCAN_PER_THREAD; k++) {
+        const uint32_t g = base + k;
+        if (g < sh.G) {
+            const uint32_t s = counts[g], t = (s + sh.L - 1) / sh.L;
+            v = v + Scan3{s, t, t > 1 ? 1u : 0u};
+        }
     }
-    if (tid == nt - 1) {
-        offsets[sh.G] = s_pts[tid];
-        task_off[sh.G] = s_tsk[tid];
-        heavy[0] = s_hvy[tid];
+    Scan3 total;
+    block_scan(v, &total);
+    if (threadIdx.x == 0) tile_sums[blockIdx.x] = total;
+}
+
+// one CTA: exclusive scan of the tile sums in place; totals to offsets[G], task_off[G], heavy[0]
+__global__ void __launch_bounds__(1024)
+msm_scan_spine_kernel(Scan3* __restrict__ tile_sums, uint32_t ntiles, MsmShape sh, uint32_t* __restrict__ offsets,
+                      uint32_t* __restrict__ task_off, uint32_t* __restrict__ heavy) {
+    const uint32_t per = (ntiles + blockDim.x - 1) / blockDim.x;
+    const uint32_t lo = min(threadIdx.x * per, ntiles), hi = min(lo + per, ntiles);
+    Scan3 v{0, 0, 0};
+    for (uint32_t i = lo; i < hi; i++) v = v + tile_sums[i];
+    Scan3 total;
+    Scan3 incl = block_scan(v, &total);
+    Scan3 run = {incl.pts - v.pts, incl.tsk - v.tsk, incl.hvy - v.hvy};
+    for (uint32_t i = lo; i < hi; i++) {
+        Scan3 t = tile_sums[i];
+        tile_sums[i] = run;
+        run = run + t;
+    }
+    if (threadIdx.x == 0) {
+        offsets[sh.G] = total.pts;
+        task_off[sh.G] = total.tsk;
+        heavy[0] = total.hvy;
+    }
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS)
+msm_scan_apply_kernel(const uint32_t* __restrict__ counts, MsmShape sh, const Scan3* __restrict__ tile_sums,
+                      uint32_t* __restrict__ offsets, uint32_t* __restrict__ task_off, uint32_t* __restrict__ heavy) {
+    const uint32_t base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_PER_THREAD;
+    uint32_t s[SCAN_PER_THREAD], t[SCAN_PER_THREAD];
+    Scan3 v{0, 0, 0};
+#pragma unroll
+    for (int k = 0; k < SCAN_PER_THREAD; k++) {
+        const uint32_t g = base + k;
+        s[k] = g < sh.G ? counts[g] : 0u;
+        t[k] = (s[k] + sh.L - 1) / sh.L;
+        v = v + Scan3{s[k], t[k], t[k] > 1 ? 1u : 0u};
+    }
+    Scan3 total;
+    Scan3 incl = block_scan(v, &total);
+    const Scan3 tb = tile_sums[blockIdx.x];
+    Scan3 run = {tb.pts + incl.pts - v.pts, tb.tsk + incl.tsk - v.tsk, tb.hvy + incl.hvy - v.hvy};
+#pragma unroll
+    for (int k = 0; k < SCAN_PER_THREAD; k++) {
+        const uint32_t g = base + k;
+        if (g < sh.G) {
+            offsets[g] = run.pts;
+            task_off[g] = run.tsk;
+            if (t[k] > 1) heavy[1 + run.hvy] = g;
+            run = run + Scan3{s[k], t[k], t[k] > 1 ? 1u : 0u};
+        }
     }
 }
 
@@ -116,14 +192,22 @@ __global__ void msm_scatter_kernel(const Fr* __restrict__ scalars, uint64_t n, b
                                    uint32_t* __restrict__ sorted) {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
+    const unsigned active = __activemask();
+    const unsigned lane = threadIdx.x & 31;
     DigitIter it;
     load_scalar(it, scalars, i, mont);
     for (uint32_t w = 0; w < sh.nwin; w++) {
         const int32_t d = it.next(w, sh.c, sh.nwin);
-        if (d == 0) continue;
-        const uint32_t g = w * sh.B + (uint32_t)(d < 0 ? -d : d) - 1;
-        const uint32_t pos = offsets[g] + atomicAdd(&cursor[g], 1u);
-        sorted[pos] = (uint32_t)i | (d < 0 ? 0x80000000u : 0u);
+        const uint32_t key = d != 0 ? w * sh.B + (uint32_t)(d < 0 ? -d : d) - 1 : 0xffffffffu;
+        const unsigned peers = __match_any_sync(active, key);
+        const unsigned leader = (unsigned)(__ffs(peers) - 1);
+        uint32_t base = 0;
+        if (key != 0xffffffffu && lane == leader) base = atomicAdd(&cursor[key], (uint32_t)__popc(peers));
+        base = __shfl_sync(peers, base, leader);
+        if (key != 0xffffffffu) {
+            const uint32_t rank = __popc(peers & ((1u << lane) - 1u));
+            sorted[offsets[key] + base + rank] = (uint32_t)i | (d < 0 ? 0x80000000u : 0u);
+        }
     }
 }
 
@@ -148,17 +232,42 @@ __device__ __forceinline__ XYZZ<F> cta_sum(const XYZZ<F>* __restrict__ pts, uint
     return smem[0];
 }
 
+// Buckets that were split into tasks: sum their task partials.  Big ones (>= HEAVY_BIG partials, e.g. the
+// one-bucket-per-window case of an all-equal witness) first get HEAVY_SPLIT CTAs each, which leave their
+// slice sums in tmp[t0 / HEAVY_SPLIT + j] (t0 = first task of the bucket; slots of different big buckets
+// cannot overlap because each owns >= HEAVY_BIG consecutive tasks); then one CTA per bucket finishes.
+static constexpr uint32_t HEAVY_SPLIT = 16;
+static constexpr uint32_t HEAVY_BIG = 16 * HEAVY_SPLIT;
+
+template <class F>
+__global__ void __launch_bounds__(MSM_RED_THREADS)
+msm_reduce_heavy_stage1_kernel(const uint32_t* __restrict__ heavy, const uint32_t* __restrict__ task_off,
+                               const XYZZ<F>* __restrict__ partials, XYZZ<F>* __restrict__ tmp) {
+    extern __shared__ uint4 smem_raw[];
+    XYZZ<F>* smem = reinterpret_cast<XYZZ<F>*>(smem_raw);
+    const uint32_t nitems = heavy[0] * HEAVY_SPLIT;
+    for (uint32_t it = blockIdx.x; it < nitems; it += gridDim.x) {
+        const uint32_t g = heavy[1 + it / HEAVY_SPLIT], j = it % HEAVY_SPLIT;
+        const uint32_t t0 = task_off[g], cnt = task_off[g + 1] - t0;
+        if (cnt < HEAVY_BIG) continue;
+        const uint32_t lo = (uint32_t)((uint64_t)cnt * j / HEAVY_SPLIT), hi = (uint32_t)((uint64_t)cnt * (j + 1) / HEAVY_SPLIT);
+        XYZZ<F> s = cta_sum(partials + t0 + lo, hi - lo, smem);
+        if (threadIdx.x == 0) st_struct(tmp + t0 / HEAVY_SPLIT + j, s);
+        __syncthreads();
+    }
+}
+
 template <class F>
 __global__ void __launch_bounds__(MSM_RED_THREADS)
 msm_reduce_heavy_kernel(const uint32_t* __restrict__ heavy, const uint32_t* __restrict__ task_off,
-                        const XYZZ<F>* __restrict__ partials, XYZZ<F>* __restrict__ bucket_acc) {
+                        const XYZZ<F>* __restrict__ partials, const XYZZ<F>* __restrict__ tmp, XYZZ<F>* __restrict__ bucket_acc) {
     extern __shared__ uint4 smem_raw[];
     XYZZ<F>* smem = reinterpret_cast<XYZZ<F>*>(smem_raw);
     const uint32_t nheavy = heavy[0];
     for (uint32_t h = blockIdx.x; h < nheavy; h += gridDim.x) {
         const uint32_t g = heavy[1 + h];
         const uint32_t t0 = task_off[g], cnt = task_off[g + 1] - t0;
-        XYZZ<F> s = cta_sum(partials + t0, cnt, smem);
+        XYZZ<F> s = cnt < HEAVY_BIG ? cta_sum(partials + t0, cnt, smem) : cta_sum(tmp + t0 / HEAVY_SPLIT, HEAVY_SPLIT, smem);
         if (threadIdx.x == 0) st_struct(bucket_acc + g, s);
         __syncthreads();
     }
@@ -176,11 +285,11 @@ __device__ __forceinline__ XYZZ<F> mul_small(const XYZZ<F>& p, uint32_t k) {
     return acc;
 }
 
-// Segment sums: thread handles buckets [s0, s0 + MSM_SEG) of one window (bucket index b is 0-based,
+// Segment sums: thread handles buckets [s0, s0 + MSM_SEG) of one window (MSM_SEG chosen by the host) (bucket index b is 0-based,
 // weight b + 1):  sum (b+1) B_b = sum_{local} (j+1) B_{s0+j} + s0 * sum B_{s0+j}.
 template <class F>
 __global__ void __launch_bounds__(128)
-msm_bucket_segments_kernel(const XYZZ<F>* __restrict__ bucket_acc, MsmShape sh, XYZZ<F>* __restrict__ seg_out) {
+msm_bucket_segments_kernel(const XYZZ<F>* __restrict__ bucket_acc, MsmShape sh, uint32_t MSM_SEG, XYZZ<F>* __restrict__ seg_out) {
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t segs_per_win = (sh.B + MSM_SEG - 1) / MSM_SEG;
     if (t >= segs_per_win * sh.nwin) return;
@@ -210,19 +319,6 @@ msm_window_sum_kernel(const XYZZ<F>* __restrict__ seg, uint32_t segs_per_win, XY
     if (threadIdx.x == 0) st_struct(win_out + blockIdx.x, s);
 }
 
-// result = sum_w 2^(c w) S_w  (Horner from the top window).
-template <class F>
-__global__ void msm_horner_kernel(const XYZZ<F>* __restrict__ win, MsmShape sh, XYZZ<F>* __restrict__ out) {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    XYZZ<F> acc = ld_struct(win + (sh.nwin - 1));
-    for (uint32_t w = sh.nwin - 1; w-- > 0;) {
-        for (uint32_t i = 0; i < sh.c; i++) acc = acc.dbl();
-        XYZZ<F> v = ld_struct(win + w);
-        acc.add(v);
-    }
-    st_struct(out, acc);
-}
-
 // sum of `count` XYZZ points -> affine (join of multi-GPU shard partials; final normalisation)
 template <class F>
 __global__ void __launch_bounds__(MSM_RED_THREADS)
@@ -242,20 +338,31 @@ static uint32_t env_u32(const char* name, uint32_t dflt) {
     return v ? (uint32_t)strtoul(v, nullptr, 10) : dflt;
 }
 
-static MsmShape msm_shape(uint64_t n, uint32_t scalar_bits) {
+// Window size: minimise  n * nwin  (bucket accumulation, mixed additions)  +  nwin * 2^(c-1) * 4.7
+// (bucket reduction: two general additions per bucket at ~1.4x the cost of a mixed one, plus the
+// per-segment double-and-add), subject to the bucket array staying under 4 GiB.
+static MsmShape msm_shape(uint64_t n, uint32_t scalar_bits, size_t point_bytes) {
     MsmShape sh{};
-    uint32_t logn = 0;
-    while ((1ull << logn) < n) logn++;
-    uint32_t c = logn > 6 ? logn - 6 : 1;
-    if (c < 5) c = 5;
-    if (c > 16) c = 16;
-    c = env_u32("B2S_MSM_C", c);
+    auto nwin_of = [&](uint32_t c) {
+        uint32_t nw = (scalar_bits + c - 1) / c;
+        // the last window keeps the recoding carry: it must fit in 2^(c-1) buckets
+        if (scalar_bits - (nw - 1) * c >= c) nw += 1;
+        return nw;
+    };
+    uint32_t best_c = 5;
+    double best = 1e300;
+    for (uint32_t c = 5; c <= 20; c++) {
+        const uint32_t nw = nwin_of(c);
+        const double buckets = (double)nw * (double)(1u << (c - 1));
+        if (buckets * (double)point_bytes > 4.0 * 1024 * 1024 * 1024) break;
+        const double cost = (double)n * nw + buckets * 4.7;
+        if (cost < best) { best = cost; best_c = c; }
+    }
+    uint32_t c = env_u32("B2S_MSM_C", best_c);
     if (c < 2) c = 2;
     if (c > 24) c = 24;
     sh.c = c;
-    sh.nwin = (scalar_bits + c - 1) / c;
-    // the last window keeps the recoding carry: it must fit in 2^(c-1) buckets
-    if (scalar_bits - (sh.nwin - 1) * c >= c) sh.nwin += 1;
+    sh.nwin = nwin_of(c);
     sh.B = 1u << (c - 1);
     sh.G = sh.nwin * sh.B;
     const uint64_t t_upper = (uint64_t)sh.nwin * n;
@@ -277,11 +384,16 @@ static int32_t msm_run_t(Ctx* c, const void* bases_dev, const void* scalars_dev,
         B2S_CUDA(c, cudaMemsetAsync(out, 0, sizeof(Pt), c->stream));
         return B2S_OK;
     }
-    const MsmShape sh = msm_shape(n, Curve::FrP::BITS);
+    const MsmShape sh = msm_shape(n, Curve::FrP::BITS, sizeof(Pt));
+    if ((uint64_t)sh.nwin * n >= (1ull << 32)) return fail(c, B2S_ERR_INVALID_ARG, "msm: n * windows exceeds 2^32");
     const Fr* scalars = reinterpret_cast<const Fr*>(scalars_dev);
     const Affine<F>* bases = reinterpret_cast<const Affine<F>*>(bases_dev);
 
-    DevBuf ibuf, sorted, bucket_acc, partials, segs, wins;
+    const uint32_t MSM_SEG = env_u32("B2S_MSM_SEG", sh.B >= (1u << 16) ? 32u : 16u);
+    const uint32_t ntiles = (sh.G + SCAN_TILE - 1) / SCAN_TILE;
+    DevBuf ibuf, sorted, bucket_acc, partials, segs, wins, tiles, heavy_tmp;
+    B2S_TRY(tiles.alloc(c, (size_t)ntiles * sizeof(Scan3)));
+    B2S_TRY(heavy_tmp.alloc(c, ((size_t)sh.max_tasks / HEAVY_SPLIT + HEAVY_SPLIT + 1) * sizeof(Pt)));
     // u32 arrays: counts[G] cursor[G] offsets[G+1] task_off[G+1] heavy[G+1]
     const size_t ints = (size_t)5 * sh.G + 3;
     B2S_TRY(ibuf.alloc(c, ints * sizeof(uint32_t)));
@@ -300,29 +412,31 @@ static int32_t msm_run_t(Ctx* c, const void* bases_dev, const void* scalars_dev,
     B2S_TRY(wins.alloc(c, (size_t)sh.nwin * sizeof(Pt)));
 
     B2S_LAUNCH(c, msm_count_kernel<Fr>, cdiv(n, 256), 256, 0, scalars, n, mont, sh, counts);
-    B2S_LAUNCH(c, msm_scan_kernel, 1, 1024, 0, counts, sh, offsets, task_off, heavy);
+    B2S_LAUNCH(c, msm_scan_tiles_kernel, ntiles, SCAN_THREADS, 0, counts, sh, tiles.as<Scan3>());
+    B2S_LAUNCH(c, msm_scan_spine_kernel, 1, 1024, 0, tiles.as<Scan3>(), ntiles, sh, offsets, task_off, heavy);
+    B2S_LAUNCH(c, msm_scan_apply_kernel, ntiles, SCAN_THREADS, 0, counts, sh, tiles.as<Scan3>(), offsets, task_off, heavy);
     B2S_LAUNCH(c, msm_scatter_kernel<Fr>, cdiv(n, 256), 256, 0, scalars, n, mont, sh, offsets, cursor, sorted.as<uint32_t>());
-    if (sizeof(F) == sizeof(typename Curve::Fq)) {
-        B2S_TRY(msm_accumulate_g1(c, bases, sorted.as<uint32_t>(), offsets, task_off, sh, bucket_acc.p, partials.p));
-    } else {
-        B2S_LAUNCH(c, msm_accumulate_kernel<F>, cdiv(sh.max_tasks, MSM_ACC_THREADS), MSM_ACC_THREADS, 0, bases,
-                   sorted.as<uint32_t>(), offsets, task_off, sh, bucket_acc.as<Pt>(), partials.as<Pt>());
-    }
+    constexpr bool is_g1 = sizeof(F) == sizeof(typename Curve::Fq);
+    if (is_g1) B2S_TRY(msm_accumulate_g1(c, bases, sorted.as<uint32_t>(), offsets, task_off, sh, bucket_acc.p, partials.p));
+    else B2S_TRY(msm_accumulate_g2(c, bases, sorted.as<uint32_t>(), offsets, task_off, sh, bucket_acc.p, partials.p));
     const size_t red_smem = (size_t)MSM_RED_THREADS * sizeof(Pt);
     static bool attr_done[2][2] = {{false, false}, {false, false}};
     constexpr int gi = sizeof(F) == sizeof(typename Curve::Fq) ? 0 : 1;
     if (!attr_done[Curve::id][gi]) {
         B2S_CUDA(c, cudaFuncSetAttribute(msm_reduce_heavy_kernel<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)red_smem));
+        B2S_CUDA(c, cudaFuncSetAttribute(msm_reduce_heavy_stage1_kernel<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)red_smem));
         B2S_CUDA(c, cudaFuncSetAttribute(msm_window_sum_kernel<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)red_smem));
         B2S_CUDA(c, cudaFuncSetAttribute(group_sum_affine_kernel<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)red_smem));
         attr_done[Curve::id][gi] = true;
     }
+    B2S_LAUNCH(c, msm_reduce_heavy_stage1_kernel<F>, 4 * c->sm_count, MSM_RED_THREADS, red_smem, heavy, task_off,
+               partials.as<Pt>(), heavy_tmp.as<Pt>());
     B2S_LAUNCH(c, msm_reduce_heavy_kernel<F>, 2 * c->sm_count, MSM_RED_THREADS, red_smem, heavy, task_off,
-               partials.as<Pt>(), bucket_acc.as<Pt>());
+               partials.as<Pt>(), heavy_tmp.as<Pt>(), bucket_acc.as<Pt>());
     B2S_LAUNCH(c, msm_bucket_segments_kernel<F>, cdiv((uint64_t)segs_per_win * sh.nwin, 128), 128, 0,
-               bucket_acc.as<Pt>(), sh, segs.as<Pt>());
+               bucket_acc.as<Pt>(), sh, MSM_SEG, segs.as<Pt>());
     B2S_LAUNCH(c, msm_window_sum_kernel<F>, sh.nwin, MSM_RED_THREADS, red_smem, segs.as<Pt>(), segs_per_win, wins.as<Pt>());
-    B2S_LAUNCH(c, msm_horner_kernel<F>, 1, 32, 0, wins.as<Pt>(), sh, out);
+    B2S_TRY(msm_horner(c, is_g1 ? 1 : 2, wins.p, sh, out));
     return B2S_OK;
 }
 

@@ -98,6 +98,27 @@ msm_accumulate_kernel(const Affine<F>* __restrict__ bases, const uint32_t* __res
 }
 
 
+// result = sum_w 2^(c w) S_w  (Horner from the top window).
+template <class F>
+__global__ void msm_horner_kernel(const XYZZ<F>* __restrict__ win, MsmShape sh, XYZZ<F>* __restrict__ out) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    XYZZ<F> acc = ld_struct(win + (sh.nwin - 1));
+    for (uint32_t w = sh.nwin - 1; w-- > 0;) {
+        for (uint32_t i = 0; i < sh.c; i++) acc = acc.dbl();
+        XYZZ<F> v = ld_struct(win + w);
+        acc.add(v);
+    }
+    st_struct(out, acc);
+}
+
+// launches compiled with the multiplication inlined: msm_acc_g1.cu (G1) and msm_acc_g2.cu (G2)
+int32_t msm_accumulate_g2(Ctx* c, const void* bases, const uint32_t* sorted, const uint32_t* offsets,
+                          const uint32_t* task_off, MsmShape sh, void* bucket_acc, void* partials);
+int32_t msm_horner_g1(Ctx* c, const void* wins, MsmShape sh, void* out);
+int32_t msm_horner_g2(Ctx* c, const void* wins, MsmShape sh, void* out);
+inline int32_t msm_horner(Ctx* c, int group, const void* wins, MsmShape sh, void* out) {
+    return group == 1 ? msm_horner_g1(c, wins, sh, out) : msm_horner_g2(c, wins, sh, out);
+}
 // G1 accumulate for the ctx's curve (msm_acc_g1.cu)
 int32_t msm_accumulate_g1(Ctx* c, const void* bases, const uint32_t* sorted, const uint32_t* offsets,
                           const uint32_t* task_off, MsmShape sh, void* bucket_acc, void* partials);

@@ -10,9 +10,17 @@ int32_t msm_accumulate_g1(Ctx* c, const void* bases, const uint32_t* sorted, con
                           const uint32_t* task_off, MsmShape sh, void* bucket_acc, void* partials) {
     return dispatch_curve(c, [&](auto curve) {
         using F = typename decltype(curve)::Fq;
-        B2S_LAUNCH(c, msm_accumulate_kernel<F>, cdiv(sh.max_tasks, MSM_ACC_THREADS), MSM_ACC_THREADS, 0,
+        B2S_LAUNCH_N(c, "msm_accumulate_g1", msm_accumulate_kernel<F>, cdiv(sh.max_tasks, MSM_ACC_THREADS), MSM_ACC_THREADS, 0,
                    reinterpret_cast<const Affine<F>*>(bases), sorted, offsets, task_off, sh,
                    reinterpret_cast<XYZZ<F>*>(bucket_acc), reinterpret_cast<XYZZ<F>*>(partials));
+        return (int32_t)B2S_OK;
+    });
+}
+
+int32_t msm_horner_g1(Ctx* c, const void* wins, MsmShape sh, void* out) {
+    return dispatch_curve(c, [&](auto curve) {
+        using F = typename decltype(curve)::Fq;
+        B2S_LAUNCH(c, msm_horner_kernel<F>, 1, 32, 0, reinterpret_cast<const XYZZ<F>*>(wins), sh, reinterpret_cast<XYZZ<F>*>(out));
         return (int32_t)B2S_OK;
     });
 }

@@ -1,0 +1,28 @@
+// G2 bucket accumulation (Fq2 = 3 Fq multiplications per product) and the G2 Horner tail, compiled
+// with the multiplication inlined: 252 registers, no spills, two CTAs of 128 threads per SM -- which
+// the micro-benchmark shows is enough warps to keep the fmaheavy pipe full (profiles/r01_microbench.txt).
+#define B2S_INLINE_MUL 1
+#include "msm_acc.cuh"
+
+namespace b2s {
+
+int32_t msm_accumulate_g2(Ctx* c, const void* bases, const uint32_t* sorted, const uint32_t* offsets,
+                          const uint32_t* task_off, MsmShape sh, void* bucket_acc, void* partials) {
+    return dispatch_curve(c, [&](auto curve) {
+        using F = typename decltype(curve)::Fq2;
+        B2S_LAUNCH_N(c, "msm_accumulate_g2", msm_accumulate_kernel<F>, cdiv(sh.max_tasks, MSM_ACC_THREADS), MSM_ACC_THREADS, 0,
+                     reinterpret_cast<const Affine<F>*>(bases), sorted, offsets, task_off, sh,
+                     reinterpret_cast<XYZZ<F>*>(bucket_acc), reinterpret_cast<XYZZ<F>*>(partials));
+        return (int32_t)B2S_OK;
+    });
+}
+
+int32_t msm_horner_g2(Ctx* c, const void* wins, MsmShape sh, void* out) {
+    return dispatch_curve(c, [&](auto curve) {
+        using F = typename decltype(curve)::Fq2;
+        B2S_LAUNCH(c, msm_horner_kernel<F>, 1, 32, 0, reinterpret_cast<const XYZZ<F>*>(wins), sh, reinterpret_cast<XYZZ<F>*>(out));
+        return (int32_t)B2S_OK;
+    });
+}
+
+}  // namespace b2s
