@@ -196,7 +196,7 @@ def run_reference(args):
         "note": "C++ restatement of the ark-ec/ark-poly/ark-groth16 algorithms (no Rust toolchain here); MSMs are chunked over "
                 "all host threads, which is stronger than ark-ec's per-window rayon parallelism",
     }
-    print(json.dumps(out), flush=True)
+    emit(out)
 
 
 def workload_config(args, world):
@@ -281,9 +281,9 @@ def run_b200(args):
                 return be.groth16_prove_resident(pk, mat, z_dev, r, s)
             return be.groth16_prove(pk, mat, zi_ptr_obj, zw_ptr_obj, r, s)
         if resident:
-            shard_fn = lambda: be.groth16_prove_shard_resident(pk, mat, z_dev)
+            shard_fn = lambda: be.groth16_prove_shard_resident(pk, mat, z_dev, r, s)
         else:
-            shard_fn = lambda: be.groth16_prove_shard(pk, mat, zi_ptr_obj, zw_ptr_obj)
+            shard_fn = lambda: be.groth16_prove_shard(pk, mat, zi_ptr_obj, zw_ptr_obj, r, s)
         # the one exchange of the path: an NCCL all-gather of 5 partial points per rank, joined on rank 0
         return shard.sharded_prove(dist, rank, world, shard_fn, lambda p1, p2, w: be.groth16_finish(pk, p1, p2, w, r, s),
                                    be.g1x_bytes // 4, be.g2x_bytes // 4, device=dev)
@@ -377,7 +377,7 @@ def run_b200(args):
         scale = (1 << log_s) / (1 << args.log_n)
         out["cpu_baseline"] = {"value": scale / sec, "unit": "proofs/s", "cores": threads, "kind": "port",
                                "sample": f"one Groth16 prove at domain 2^{log_s} ({sec:.3f} s on {threads} threads), scaled linearly to 2^{args.log_n}"}
-    print(json.dumps(out), flush=True)
+    emit(out)
     if world > 1:
         dist.destroy_process_group()
 
@@ -435,6 +435,13 @@ def _gen_limbs():
 
 
 _G1_GEN_MONT, _G2_GEN_MONT = _gen_limbs()
+_REAL_STDOUT = None
+
+
+def emit(obj):
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(obj) + "\n")
+    out.flush()
 
 
 def main():
@@ -448,6 +455,12 @@ def main():
     ap.add_argument("--no-extras", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
+    # the contract is ONE JSON line on stdout: anything libraries print there (e.g. NCCL's version banner) goes
+    # to stderr instead; emit() writes the result line to the real stdout
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     if args.impl == "reference":
         run_reference(args)
     else:

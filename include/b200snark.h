@@ -156,12 +156,14 @@ int32_t b2s_groth16_prove(b2s_ctx* ctx, const b2s_pk* pk, const b2s_r1cs* m, con
 int32_t b2s_groth16_prove_resident(b2s_ctx* ctx, const b2s_pk* pk, const b2s_r1cs* m, const void* z_dev, const void* r,
                                    const void* s, void* out_a_g1, void* out_b_g2, void* out_c_g1);
 /* Shard step for multi-GPU: computes this shard's five MSM partial sums
- *   out_partials = [ h_acc, l_acc, a_acc, b1_acc ] (4 G1 XYZZ) and out_b2_partial (1 G2 XYZZ), HOST. */
+ *   out_partials = [ h_acc, l_acc, a_acc, b1_acc ] (4 G1 XYZZ) and out_b2_partial (1 G2 XYZZ), HOST.
+ * r, s are needed here too: the shard that owns the end of a query range folds r*delta / s*delta into its MSMs. */
 int32_t b2s_groth16_prove_shard(b2s_ctx* ctx, const b2s_pk* pk, const b2s_r1cs* m, const void* z_instance,
-                                const void* z_witness, void* out_g1_partials, void* out_g2_partial);
+                                const void* z_witness, const void* r, const void* s, void* out_g1_partials,
+                                void* out_g2_partial);
 /* Same with z resident on the GPU. */
-int32_t b2s_groth16_prove_shard_resident(b2s_ctx* ctx, const b2s_pk* pk, const b2s_r1cs* m, const void* z_dev,
-                                         void* out_g1_partials, void* out_g2_partial);
+int32_t b2s_groth16_prove_shard_resident(b2s_ctx* ctx, const b2s_pk* pk, const b2s_r1cs* m, const void* z_dev, const void* r,
+                                         const void* s, void* out_g1_partials, void* out_g2_partial);
 /* Join: sums the per-shard partials (n_shards x 4 G1 XYZZ, n_shards G2 XYZZ) and applies the r/s epilogue. */
 int32_t b2s_groth16_finish(b2s_ctx* ctx, const b2s_pk* pk, const void* g1_partials, const void* g2_partials,
                            uint32_t n_shards, const void* r, const void* s, void* out_a_g1, void* out_b_g2,

@@ -21,6 +21,9 @@
 // Threading: ark-ec parallelises an MSM over its <= 17 windows with rayon; here the points are also cut
 // into one chunk per thread so that all host cores work (a stronger baseline than the reference's own).
 #include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <cstdint>
 #include <functional>
 #include <cstring>
@@ -405,6 +408,18 @@ static void run_parallel(int threads, int jobs, const std::function<void(int)>& 
     for (auto& t : th) t.join();
 }
 
+// optional phase timing on stderr (ORC_TIMING=1)
+struct PhaseTimer {
+    std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+    bool on = getenv("ORC_TIMING") != nullptr;
+    void lap(const char* what) {
+        if (!on) return;
+        auto t1 = std::chrono::steady_clock::now();
+        fprintf(stderr, "[oracle] %-12s %.3f s\n", what, std::chrono::duration<double>(t1 - t0).count());
+        t0 = t1;
+    }
+};
+
 // ---- curve instantiation -----------------------------------------------------------------------
 typedef Fp<6, 0> BlsFq;
 typedef Fp<4, 1> BlsFr;
@@ -457,15 +472,20 @@ static void prove_t(const FrConsts<Fr>& K, int num_bits, const Csr mats[3], size
     std::vector<Fr> z(n_vars), h(N);
     memcpy(z.data(), z_inst, n_inst * sizeof(Fr));
     memcpy(z.data() + n_inst, z_wit, n_wit * sizeof(Fr));
+    PhaseTimer pt;
     witness_map(mats, n_rows, n_inst, z.data(), log_dom, h.data(), K, threads);
+    pt.lap("witness_map");
     if (out_h) memcpy(out_h, h.data(), N * sizeof(Fr));
     J1 h_acc = msm<Fq, Fr>(hq, h.data(), N - 1, true, threads, num_bits);
+    pt.lap("msm h");
     J1 l_acc = msm<Fq, Fr>(lq, z.data() + n_inst, n_wit, true, threads, num_bits);
+    pt.lap("msm l");
     Fr rc = r->from_mont(), sc = s->from_mont(), rsc = (*r * *s).from_mont();
     // calculate_coeff: r * delta + query[0] + msm(query[1..], z[1..]) + vk_param
     J1 g_a = J1::from_affine(*delta1).mul(rc.v, 4).add_affine(aq[0]).add(msm<Fq, Fr>(aq + 1, z.data() + 1, n_vars - 1, true, threads, num_bits)).add_affine(*alpha);
     J1 g1_b = J1::from_affine(*delta1).mul(sc.v, 4).add_affine(b1q[0]).add(msm<Fq, Fr>(b1q + 1, z.data() + 1, n_vars - 1, true, threads, num_bits)).add_affine(*beta1);
     J2 g2_b = J2::from_affine(*delta2).mul(sc.v, 4).add_affine(b2q[0]).add(msm<Fq2, Fr>(b2q + 1, z.data() + 1, n_vars - 1, true, threads, num_bits)).add_affine(*beta2);
+    pt.lap("msm a,b1,b2");
     J1 g_c = g_a.mul(sc.v, 4).add(g1_b.mul(rc.v, 4)).add(J1::from_affine(*delta1).mul(rsc.v, 4).neg()).add(l_acc).add(h_acc);
     A1 oa = g_a.to_affine(), oc = g_c.to_affine();
     A2 ob = g2_b.to_affine();

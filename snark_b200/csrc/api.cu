@@ -47,7 +47,13 @@ int32_t b2s_ctx_create(int32_t curve_id, int32_t device_ordinal, b2s_ctx** out) 
     c->curve = curve_id;
     c->device = device_ordinal;
     c->sm_count = prop.multiProcessorCount;
-    if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return B2S_ERR_CUDA; }
+    if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&c->aux, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&c->ev_tail, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&c->ev_done, cudaEventDisableTiming) != cudaSuccess) {
+        delete c;
+        return B2S_ERR_CUDA;
+    }
     // keep freed blocks in the stream-ordered pool: proofs reuse the same multi-GiB scratch every call
     cudaMemPool_t pool;
     if (cudaDeviceGetDefaultMemPool(&pool, device_ordinal) == cudaSuccess) {
@@ -65,6 +71,10 @@ void b2s_ctx_destroy(b2s_ctx* ctx) {
     ntt_free_plans(ctx);
     fixed_base_free(ctx);
     cudaStreamSynchronize(ctx->stream);
+    cudaStreamSynchronize(ctx->aux);
+    cudaEventDestroy(ctx->ev_tail);
+    cudaEventDestroy(ctx->ev_done);
+    cudaStreamDestroy(ctx->aux);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -295,17 +305,18 @@ void b2s_pk_free(b2s_ctx* ctx, b2s_pk* pk) {
 }
 
 int32_t b2s_groth16_prove_shard(b2s_ctx* ctx, const b2s_pk* pk, const b2s_r1cs* m, const void* z_instance,
-                                const void* z_witness, void* out_g1_partials, void* out_g2_partial) {
+                                const void* z_witness, const void* r, const void* s, void* out_g1_partials,
+                                void* out_g2_partial) {
     LOCK(ctx);
     if (!pk || !m) return fail(ctx, B2S_ERR_MISSING_CS, "prove_shard: null key or matrices");
-    if (!z_instance || (!z_witness && m->n_witness) || !out_g1_partials || !out_g2_partial)
+    if (!z_instance || (!z_witness && m->n_witness) || !r || !s || !out_g1_partials || !out_g2_partial)
         return fail(ctx, B2S_ERR_ASSIGNMENT_MISSING, "prove_shard: null assignment or output");
     uint32_t sz[6];
     sizes_for(ctx->curve, sz);
     DevBuf g1, g2;
     B2S_TRY(g1.alloc(ctx, 4 * sz[4]));
     B2S_TRY(g2.alloc(ctx, sz[5]));
-    B2S_TRY(groth16_shard(ctx, pk, m, z_instance, z_witness, nullptr, g1.p, g2.p));
+    B2S_TRY(groth16_shard(ctx, pk, m, z_instance, z_witness, nullptr, r, s, g1.p, g2.p));
     B2S_CUDA(ctx, cudaMemcpyAsync(out_g1_partials, g1.p, 4 * sz[4], cudaMemcpyDeviceToHost, ctx->stream));
     B2S_CUDA(ctx, cudaMemcpyAsync(out_g2_partial, g2.p, sz[5], cudaMemcpyDeviceToHost, ctx->stream));
     B2S_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -338,7 +349,7 @@ int32_t b2s_groth16_prove(b2s_ctx* ctx, const b2s_pk* pk, const b2s_r1cs* m, con
     DevBuf g1, g2;
     B2S_TRY(g1.alloc(ctx, 4 * sz[4]));
     B2S_TRY(g2.alloc(ctx, sz[5]));
-    B2S_TRY(groth16_shard(ctx, pk, m, z_instance, z_witness, nullptr, g1.p, g2.p));
+    B2S_TRY(groth16_shard(ctx, pk, m, z_instance, z_witness, nullptr, r, s, g1.p, g2.p));
     return groth16_finish(ctx, pk, g1.p, g2.p, 1, r, s, out_a_g1, out_b_g2, out_c_g1);
 }
 
@@ -355,21 +366,21 @@ int32_t b2s_groth16_prove_resident(b2s_ctx* ctx, const b2s_pk* pk, const b2s_r1c
     DevBuf g1, g2;
     B2S_TRY(g1.alloc(ctx, 4 * sz[4]));
     B2S_TRY(g2.alloc(ctx, sz[5]));
-    B2S_TRY(groth16_shard(ctx, pk, m, nullptr, nullptr, z_dev, g1.p, g2.p));
+    B2S_TRY(groth16_shard(ctx, pk, m, nullptr, nullptr, z_dev, r, s, g1.p, g2.p));
     return groth16_finish(ctx, pk, g1.p, g2.p, 1, r, s, out_a_g1, out_b_g2, out_c_g1);
 }
 
-int32_t b2s_groth16_prove_shard_resident(b2s_ctx* ctx, const b2s_pk* pk, const b2s_r1cs* m, const void* z_dev,
-                                         void* out_g1_partials, void* out_g2_partial) {
+int32_t b2s_groth16_prove_shard_resident(b2s_ctx* ctx, const b2s_pk* pk, const b2s_r1cs* m, const void* z_dev, const void* r,
+                                         const void* s, void* out_g1_partials, void* out_g2_partial) {
     LOCK(ctx);
     if (!pk || !m) return fail(ctx, B2S_ERR_MISSING_CS, "prove_shard: null key or matrices");
-    if (!z_dev || !out_g1_partials || !out_g2_partial) return fail(ctx, B2S_ERR_ASSIGNMENT_MISSING, "prove_shard: null argument");
+    if (!z_dev || !r || !s || !out_g1_partials || !out_g2_partial) return fail(ctx, B2S_ERR_ASSIGNMENT_MISSING, "prove_shard: null argument");
     uint32_t sz[6];
     sizes_for(ctx->curve, sz);
     DevBuf g1, g2;
     B2S_TRY(g1.alloc(ctx, 4 * sz[4]));
     B2S_TRY(g2.alloc(ctx, sz[5]));
-    B2S_TRY(groth16_shard(ctx, pk, m, nullptr, nullptr, z_dev, g1.p, g2.p));
+    B2S_TRY(groth16_shard(ctx, pk, m, nullptr, nullptr, z_dev, r, s, g1.p, g2.p));
     B2S_CUDA(ctx, cudaMemcpyAsync(out_g1_partials, g1.p, 4 * sz[4], cudaMemcpyDeviceToHost, ctx->stream));
     B2S_CUDA(ctx, cudaMemcpyAsync(out_g2_partial, g2.p, sz[5], cudaMemcpyDeviceToHost, ctx->stream));
     B2S_CUDA(ctx, cudaStreamSynchronize(ctx->stream));

@@ -23,6 +23,10 @@ struct Ctx {
     int curve = 0;
     int device = 0;
     cudaStream_t stream = nullptr;
+    // second stream for latency-bound MSM tails (Horner) so they overlap the next MSM's bucket work
+    cudaStream_t aux = nullptr;
+    cudaEvent_t ev_tail = nullptr, ev_done = nullptr;
+    bool aux_pending = false;
     std::mutex mu;
     std::string err;
     uint64_t launches = 0;
@@ -61,18 +65,20 @@ inline int32_t fail(Ctx* c, int32_t code, const char* fmt, ...) {
 
 // Launch + count + check.  Usage: B2S_LAUNCH(ctx, kernel<T>, grid, block, smem, args...)
 #define B2S_LAUNCH(ctx, kern, grid, block, smem, ...) B2S_LAUNCH_N(ctx, #kern, kern, grid, block, smem, __VA_ARGS__)
-#define B2S_LAUNCH_N(ctx, label, kern, grid, block, smem, ...)                          \
+#define B2S_LAUNCH_N(ctx, label, kern, grid, block, smem, ...) \
+    B2S_LAUNCH_SN(ctx, (ctx)->stream, label, kern, grid, block, smem, __VA_ARGS__)
+#define B2S_LAUNCH_SN(ctx, strm, label, kern, grid, block, smem, ...)                   \
     do {                                                                                \
         ::b2s::Ctx::ProfRec pr__{label, nullptr, nullptr};                              \
         if ((ctx)->profiling) {                                                         \
             cudaEventCreate(&pr__.e0);                                                  \
             cudaEventCreate(&pr__.e1);                                                  \
-            cudaEventRecord(pr__.e0, (ctx)->stream);                                    \
+            cudaEventRecord(pr__.e0, (strm));                                    \
         }                                                                               \
-        kern<<<(grid), (block), (smem), (ctx)->stream>>>(__VA_ARGS__);                  \
+        kern<<<(grid), (block), (smem), (strm)>>>(__VA_ARGS__);                  \
         (ctx)->launches++;                                                              \
         if ((ctx)->profiling) {                                                         \
-            cudaEventRecord(pr__.e1, (ctx)->stream);                                    \
+            cudaEventRecord(pr__.e1, (strm));                                    \
             (ctx)->prof.push_back(pr__);                                                \
         }                                                                               \
         B2S_CUDA(ctx, cudaGetLastError());                                              \
@@ -139,8 +145,12 @@ inline int32_t dispatch_curve(Ctx* c, F&& f) {
 // ---- entry points implemented per translation unit (all take the ctx lock in api.cu) -----------
 int32_t ntt_run(Ctx* c, void* data_dev, uint32_t log_n, bool inverse, bool coset);
 void ntt_free_plans(Ctx* c);
+// wins_ext == nullptr: the whole MSM runs on c->stream.  Otherwise wins_ext is caller-owned scratch for the
+// window sums (>= 64 XYZZ points, alive until msm_join_tails): the Horner tail is queued on c->aux and the
+// caller must call msm_join_tails(c) before reading out_xyzz_dev on c->stream.
 int32_t msm_run(Ctx* c, int group, const void* bases_dev, const void* scalars_dev, uint64_t n, bool scalars_mont,
-                void* out_xyzz_dev);
+                void* out_xyzz_dev, void* wins_ext = nullptr);
+int32_t msm_join_tails(Ctx* c);
 int32_t group_sum_to_affine(Ctx* c, int group, const void* xyzz_dev, uint32_t count, void* out_affine_dev);
 
 }  // namespace b2s

@@ -6,21 +6,25 @@
 //
 //   h      = witness_map(A, B, C, z)                                        (r1cs.cu)
 //   h_acc  = MSM(h_query, h[0 .. N-1))          l_acc = MSM(l_query, z_witness)
-//   a_acc  = MSM(a_query, z)   b1_acc = MSM(b_g1_query, z)   b2_acc = MSM(b_g2_query, z)
-//   A  = alpha_1 + a_acc  + r delta_1          B2 = beta_2 + b2_acc + s delta_2
-//   B1 = beta_1  + b1_acc + s delta_1          C  = s A + r B1 - (r s) delta_1 + l_acc + h_acc
-// (ark adds query[0] separately because z[0] = 1; including index 0 in the MSM is the same group
-// element.)  For multi-GPU the five MSMs are cut by base range: each rank holds a shard of the key,
-// returns five XYZZ partial sums, and the join adds them before the epilogue (EC addition is not an
-// NCCL reduction, so the exchange is an all-gather of 5 small points).
+//   a_acc  = MSM(a_query ++ [delta_1, O], z ++ [r, s])      = sum z_j a_j + r delta_1
+//   b1_acc = MSM(b_g1_query ++ [O, delta_1], z ++ [r, s])   = sum z_j b_j + s delta_1
+//   b2_acc = MSM(b_g2_query ++ [O, delta_2], z ++ [r, s])   = sum z_j b_j + s delta_2      (G2)
+//   A = alpha_1 + a_acc      B1 = beta_1 + b1_acc      B2 = beta_2 + b2_acc
+//   C = s A + r B1 - (r s) delta_1 + l_acc + h_acc
+// ark adds query[0] and r*delta / s*delta separately (z[0] = 1, fresh r, s); putting them into the MSMs as
+// two extra (base, scalar) pairs is the same group element and removes three 255-bit scalar multiplications
+// (one of them in G2) from the latency-bound tail.  What remains serial is s*A, r*B1, (rs)*delta_1, run
+// side by side in three warps.
+//
+// Multi-GPU: the five MSMs are cut by base range; each rank holds a shard of the key and returns five XYZZ
+// partial sums; the rank that owns the END of a query range also owns its two extra pairs.  The join adds
+// the partials (EC addition is not an NCCL reduction, so the exchange is an all-gather of 5 small points)
+// and applies the epilogue.
 #include "r1cs.cuh"
 
 namespace b2s {
 
-template <class F>
-__device__ __forceinline__ void st_pt(Affine<F>* p, const Affine<F>& v) { *p = v; }
-
-// Threads 0, 32, 64 (three warps) run the independent scalar multiplications side by side.
+// Warps 0, 1, 2 run the three remaining scalar multiplications side by side.
 template <class Curve>
 __global__ void groth16_epilogue_g1_kernel(const Affine<typename Curve::Fq>* consts /*alpha,beta,delta*/,
                                            const XYZZ<typename Curve::Fq>* sums /*h,l,a,b1*/, const typename Curve::Fr* rs,
@@ -31,48 +35,39 @@ __global__ void groth16_epilogue_g1_kernel(const Affine<typename Curve::Fq>* con
     __shared__ P sh[3];
     const int role = threadIdx.x >> 5;
     const bool lead = (threadIdx.x & 31) == 0;
-    Fr r = rs[0].from_mont(), s = rs[1].from_mont();
-    Fr rsp = (rs[0] * rs[1]).from_mont();
-    const P delta = P::from_affine(consts[2]);
-    if (lead) {
-        if (role == 0) sh[0] = scalar_mul_words(delta, r.v, Fr::N);
-        if (role == 1) sh[1] = scalar_mul_words(delta, s.v, Fr::N);
-        if (role == 2) sh[2] = scalar_mul_words(delta, rsp.v, Fr::N);
+    if (lead && role == 0) {   // s * A,  A = alpha + a_acc
+        P a = sums[2];
+        a.add_affine(consts[0]);
+        *out_a = a.to_affine();
+        Fr s = rs[1].from_mont();
+        sh[0] = scalar_mul_words(a, s.v, Fr::N);
+    }
+    if (lead && role == 1) {   // r * B1,  B1 = beta + b1_acc
+        P b = sums[3];
+        b.add_affine(consts[1]);
+        Fr r = rs[0].from_mont();
+        sh[1] = scalar_mul_words(b, r.v, Fr::N);
+    }
+    if (lead && role == 2) {   // (r s) * delta
+        Fr rsp = (rs[0] * rs[1]).from_mont();
+        sh[2] = scalar_mul_words(P::from_affine(consts[2]), rsp.v, Fr::N);
     }
     __syncthreads();
-    P acc = P::identity();
-    if (lead && role == 0) {   // A
-        acc = sh[0]; acc.add(sums[2]); acc.add_affine(consts[0]);
-        sh[0] = acc;
-    }
-    if (lead && role == 1) {   // B1
-        acc = sh[1]; acc.add(sums[3]); acc.add_affine(consts[1]);
-        sh[1] = acc;
-    }
-    __syncthreads();
-    if (lead && role == 0) { P t = scalar_mul_words(sh[0], s.v, Fr::N); acc = sh[0]; sh[0] = t; *out_a = acc.to_affine(); }
-    if (lead && role == 1) { sh[1] = scalar_mul_words(sh[1], r.v, Fr::N); }
-    __syncthreads();
-    if (lead && role == 0) {
-        P cacc = sh[0];
-        cacc.add(sh[1]);
-        cacc.add(sh[2].neg());
-        cacc.add(sums[1]);
-        cacc.add(sums[0]);
-        *out_c = cacc.to_affine();
+    if (threadIdx.x == 0) {
+        P c = sh[0];
+        c.add(sh[1]);
+        c.add(sh[2].neg());
+        c.add(sums[1]);
+        c.add(sums[0]);
+        *out_c = c.to_affine();
     }
 }
 
 template <class Curve>
 __global__ void groth16_epilogue_g2_kernel(const Affine<typename Curve::Fq2>* consts /*beta,delta*/,
-                                           const XYZZ<typename Curve::Fq2>* b2_sum, const typename Curve::Fr* rs,
-                                           Affine<typename Curve::Fq2>* out_b) {
-    using Fq2 = typename Curve::Fq2;
-    using Fr = typename Curve::Fr;
+                                           const XYZZ<typename Curve::Fq2>* b2_sum, Affine<typename Curve::Fq2>* out_b) {
     if (threadIdx.x != 0) return;
-    Fr s = rs[1].from_mont();
-    XYZZ<Fq2> acc = scalar_mul_words(XYZZ<Fq2>::from_affine(consts[1]), s.v, Fr::N);
-    acc.add(b2_sum[0]);
+    XYZZ<typename Curve::Fq2> acc = b2_sum[0];
     acc.add_affine(consts[0]);
     *out_b = acc.to_affine();
 }
@@ -87,11 +82,16 @@ __global__ void sum_shards_kernel(const XYZZ<F>* partials, uint32_t n_shards, ui
     sums[j] = acc;
 }
 
-static int32_t copy_in(Ctx* c, DevBuf& dst, const void* src, size_t bytes, int32_t mem) {
-    B2S_TRY(dst.alloc(c, bytes));
-    if (bytes)
-        B2S_CUDA(c, cudaMemcpyAsync(dst.p, src, bytes, mem == B2S_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice,
-                                    c->stream));
+// query ++ extras: `len` points from src, then (if this shard owns the end of the range) two extra points
+static int32_t copy_query(Ctx* c, DevBuf& dst, const void* src, uint64_t len, size_t pt, int32_t mem, const void* extra0,
+                          const void* extra1, cudaMemcpyKind kind) {
+    B2S_TRY(dst.alloc(c, (len + 2) * pt));
+    char* d = dst.as<char>();
+    if (len) B2S_CUDA(c, cudaMemcpyAsync(d, src, len * pt, kind, c->stream));
+    B2S_CUDA(c, cudaMemsetAsync(d + len * pt, 0, 2 * pt, c->stream));   // O = all-zero bytes
+    if (extra0) B2S_CUDA(c, cudaMemcpyAsync(d + len * pt, extra0, pt, kind, c->stream));
+    if (extra1) B2S_CUDA(c, cudaMemcpyAsync(d + (len + 1) * pt, extra1, pt, kind, c->stream));
+    (void)mem;
     return B2S_OK;
 }
 
@@ -109,24 +109,30 @@ int32_t pk_upload(Ctx* c, const b2s_pk_desc* d, int32_t mem, b2s_pk** out) {
     pk->a_off = d->a_off; pk->a_len = d->a_len; pk->b1_off = d->b1_off; pk->b1_len = d->b1_len;
     pk->b2_off = d->b2_off; pk->b2_len = d->b2_len; pk->h_off = d->h_off; pk->h_len = d->h_len;
     pk->l_off = d->l_off; pk->l_len = d->l_len;
-    int32_t st = pk->consts_g1.alloc(c, 3 * g1);
-    if (st == B2S_OK) st = pk->consts_g2.alloc(c, 2 * g2);
+    pk->a_ext = (d->a_off + d->a_len == n_vars) ? 2 : 0;
+    pk->b1_ext = (d->b1_off + d->b1_len == n_vars) ? 2 : 0;
+    pk->b2_ext = (d->b2_off + d->b2_len == n_vars) ? 2 : 0;
     const cudaMemcpyKind kind = mem == B2S_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
-    if (st == B2S_OK) {
+    auto body = [&]() -> int32_t {
+        B2S_TRY(pk->consts_g1.alloc(c, 3 * g1));
+        B2S_TRY(pk->consts_g2.alloc(c, 2 * g2));
         char* p1 = pk->consts_g1.as<char>();
         char* p2 = pk->consts_g2.as<char>();
-        cudaMemcpyAsync(p1, d->alpha_g1, g1, kind, c->stream);
-        cudaMemcpyAsync(p1 + g1, d->beta_g1, g1, kind, c->stream);
-        cudaMemcpyAsync(p1 + 2 * g1, d->delta_g1, g1, kind, c->stream);
-        cudaMemcpyAsync(p2, d->beta_g2, g2, kind, c->stream);
-        cudaMemcpyAsync(p2 + g2, d->delta_g2, g2, kind, c->stream);
-    }
-    if (st == B2S_OK) st = copy_in(c, pk->a_query, d->a_query, d->a_len * g1, mem);
-    if (st == B2S_OK) st = copy_in(c, pk->b_g1_query, d->b_g1_query, d->b1_len * g1, mem);
-    if (st == B2S_OK) st = copy_in(c, pk->b_g2_query, d->b_g2_query, d->b2_len * g2, mem);
-    if (st == B2S_OK) st = copy_in(c, pk->h_query, d->h_query, d->h_len * g1, mem);
-    if (st == B2S_OK) st = copy_in(c, pk->l_query, d->l_query, d->l_len * g1, mem);
-    if (st == B2S_OK && cudaStreamSynchronize(c->stream) != cudaSuccess) st = fail(c, B2S_ERR_CUDA, "pk upload failed");
+        B2S_CUDA(c, cudaMemcpyAsync(p1, d->alpha_g1, g1, kind, c->stream));
+        B2S_CUDA(c, cudaMemcpyAsync(p1 + g1, d->beta_g1, g1, kind, c->stream));
+        B2S_CUDA(c, cudaMemcpyAsync(p1 + 2 * g1, d->delta_g1, g1, kind, c->stream));
+        B2S_CUDA(c, cudaMemcpyAsync(p2, d->beta_g2, g2, kind, c->stream));
+        B2S_CUDA(c, cudaMemcpyAsync(p2 + g2, d->delta_g2, g2, kind, c->stream));
+        // extras: a: [delta_1, O] (scalars r, s)   b1: [O, delta_1]   b2: [O, delta_2]
+        B2S_TRY(copy_query(c, pk->a_query, d->a_query, d->a_len, g1, mem, pk->a_ext ? d->delta_g1 : nullptr, nullptr, kind));
+        B2S_TRY(copy_query(c, pk->b_g1_query, d->b_g1_query, d->b1_len, g1, mem, nullptr, pk->b1_ext ? d->delta_g1 : nullptr, kind));
+        B2S_TRY(copy_query(c, pk->b_g2_query, d->b_g2_query, d->b2_len, g2, mem, nullptr, pk->b2_ext ? d->delta_g2 : nullptr, kind));
+        B2S_TRY(copy_query(c, pk->h_query, d->h_query, d->h_len, g1, mem, nullptr, nullptr, kind));
+        B2S_TRY(copy_query(c, pk->l_query, d->l_query, d->l_len, g1, mem, nullptr, nullptr, kind));
+        B2S_CUDA(c, cudaStreamSynchronize(c->stream));
+        return B2S_OK;
+    };
+    const int32_t st = body();
     if (st != B2S_OK) { delete pk; return st; }
     *out = pk;
     return B2S_OK;
@@ -134,39 +140,51 @@ int32_t pk_upload(Ctx* c, const b2s_pk_desc* d, int32_t mem, b2s_pk** out) {
 
 template <class Curve>
 static int32_t shard_t(Ctx* c, const b2s_pk* pk, const b2s_r1cs* m, const void* z_inst, const void* z_wit, const void* z_dev,
-                       void* g1_out, void* g2_out) {
+                       const void* r_host, const void* s_host, void* g1_out, void* g2_out) {
     using Fr = typename Curve::Fr;
     using P1 = XYZZ<typename Curve::Fq>;
+    using P2 = XYZZ<typename Curve::Fq2>;
     const uint64_t N = 1ull << m->log_domain;
     if (pk->n_instance != m->n_instance || pk->n_witness != m->n_witness || pk->domain_size != N)
         return fail(c, B2S_ERR_ASSIGNMENT_MISSING, "prove: key (%llu,%llu,%llu) does not match matrices (%llu,%llu,%llu)",
                     (unsigned long long)pk->n_instance, (unsigned long long)pk->n_witness, (unsigned long long)pk->domain_size,
                     (unsigned long long)m->n_instance, (unsigned long long)m->n_witness, (unsigned long long)N);
     const uint64_t n_vars = m->n_instance + m->n_witness;
-    DevBuf z, h;
+    // z_ext = z ++ [r, s]
+    DevBuf z, h, tails;
+    B2S_TRY(z.alloc(c, (n_vars + 2) * sizeof(Fr)));
     B2S_TRY(h.alloc(c, N * sizeof(Fr)));
-    const Fr* zd = reinterpret_cast<const Fr*>(z_dev);
-    if (!zd) {
-        B2S_TRY(z.alloc(c, n_vars * sizeof(Fr)));
-        Fr* zw = z.as<Fr>();
-        B2S_CUDA(c, cudaMemcpyAsync(zw, z_inst, m->n_instance * sizeof(Fr), cudaMemcpyHostToDevice, c->stream));
+    B2S_TRY(tails.alloc(c, 4 * 64 * sizeof(P1) + 64 * sizeof(P2)));
+    Fr* zd = z.as<Fr>();
+    if (z_dev) {
+        B2S_CUDA(c, cudaMemcpyAsync(zd, z_dev, n_vars * sizeof(Fr), cudaMemcpyDeviceToDevice, c->stream));
+    } else {
+        B2S_CUDA(c, cudaMemcpyAsync(zd, z_inst, m->n_instance * sizeof(Fr), cudaMemcpyHostToDevice, c->stream));
         if (m->n_witness)
-            B2S_CUDA(c, cudaMemcpyAsync(zw + m->n_instance, z_wit, m->n_witness * sizeof(Fr), cudaMemcpyHostToDevice, c->stream));
-        zd = zw;
+            B2S_CUDA(c, cudaMemcpyAsync(zd + m->n_instance, z_wit, m->n_witness * sizeof(Fr), cudaMemcpyHostToDevice, c->stream));
     }
-    B2S_TRY(witness_map_run(c, m, zd, h.p));
+    B2S_CUDA(c, cudaMemcpyAsync(zd + n_vars, r_host, sizeof(Fr), cudaMemcpyHostToDevice, c->stream));
+    B2S_CUDA(c, cudaMemcpyAsync(zd + n_vars + 1, s_host, sizeof(Fr), cudaMemcpyHostToDevice, c->stream));
     P1* g1 = reinterpret_cast<P1*>(g1_out);
-    B2S_TRY(msm_run(c, 1, pk->h_query.p, h.as<Fr>() + pk->h_off, pk->h_len, true, g1 + 0));
-    B2S_TRY(msm_run(c, 1, pk->l_query.p, zd + m->n_instance + pk->l_off, pk->l_len, true, g1 + 1));
-    B2S_TRY(msm_run(c, 1, pk->a_query.p, zd + pk->a_off, pk->a_len, true, g1 + 2));
-    B2S_TRY(msm_run(c, 1, pk->b_g1_query.p, zd + pk->b1_off, pk->b1_len, true, g1 + 3));
-    B2S_TRY(msm_run(c, 2, pk->b_g2_query.p, zd + pk->b2_off, pk->b2_len, true, g2_out));
+    P1* w1 = tails.as<P1>();
+    void* w2 = w1 + 4 * 64;
+    // the MSMs that only need z go first (their Horner tails run on the aux stream under the following work);
+    // G2 first because its tail is the longest
+    B2S_TRY(msm_run(c, 2, pk->b_g2_query.p, zd + pk->b2_off, pk->b2_len + pk->b2_ext, true, g2_out, w2));
+    B2S_TRY(msm_run(c, 1, pk->a_query.p, zd + pk->a_off, pk->a_len + pk->a_ext, true, g1 + 2, w1 + 2 * 64));
+    B2S_TRY(msm_run(c, 1, pk->b_g1_query.p, zd + pk->b1_off, pk->b1_len + pk->b1_ext, true, g1 + 3, w1 + 3 * 64));
+    B2S_TRY(msm_run(c, 1, pk->l_query.p, zd + m->n_instance + pk->l_off, pk->l_len, true, g1 + 1, w1 + 1 * 64));
+    B2S_TRY(witness_map_run(c, m, zd, h.p));
+    B2S_TRY(msm_run(c, 1, pk->h_query.p, h.as<Fr>() + pk->h_off, pk->h_len, true, g1 + 0, w1 + 0 * 64));
+    B2S_TRY(msm_join_tails(c));
     return B2S_OK;
 }
 
 int32_t groth16_shard(Ctx* c, const b2s_pk* pk, const b2s_r1cs* m, const void* z_inst, const void* z_wit, const void* z_dev,
-                      void* g1_out, void* g2_out) {
-    return dispatch_curve(c, [&](auto curve) { return shard_t<decltype(curve)>(c, pk, m, z_inst, z_wit, z_dev, g1_out, g2_out); });
+                      const void* r_host, const void* s_host, void* g1_out, void* g2_out) {
+    return dispatch_curve(c, [&](auto curve) {
+        return shard_t<decltype(curve)>(c, pk, m, z_inst, z_wit, z_dev, r_host, s_host, g1_out, g2_out);
+    });
 }
 
 template <class Curve>
@@ -188,7 +206,7 @@ static int32_t finish_t(Ctx* c, const b2s_pk* pk, const void* g1_partials, const
     char* o = outs.as<char>();
     B2S_LAUNCH(c, groth16_epilogue_g1_kernel<Curve>, 1, 96, 0, pk->consts_g1.as<Affine<Fq>>(), sums1.as<XYZZ<Fq>>(), rs.as<Fr>(),
                reinterpret_cast<Affine<Fq>*>(o), reinterpret_cast<Affine<Fq>*>(o + g1));
-    B2S_LAUNCH(c, groth16_epilogue_g2_kernel<Curve>, 1, 32, 0, pk->consts_g2.as<Affine<Fq2>>(), sums2.as<XYZZ<Fq2>>(), rs.as<Fr>(),
+    B2S_LAUNCH(c, groth16_epilogue_g2_kernel<Curve>, 1, 32, 0, pk->consts_g2.as<Affine<Fq2>>(), sums2.as<XYZZ<Fq2>>(),
                reinterpret_cast<Affine<Fq2>*>(o + 2 * g1));
     B2S_CUDA(c, cudaMemcpyAsync(out_a, o, g1, cudaMemcpyDeviceToHost, c->stream));
     B2S_CUDA(c, cudaMemcpyAsync(out_c, o + g1, g1, cudaMemcpyDeviceToHost, c->stream));

@@ -375,7 +375,7 @@ static MsmShape msm_shape(uint64_t n, uint32_t scalar_bits, size_t point_bytes) 
 }
 
 template <class Curve, class F>
-static int32_t msm_run_t(Ctx* c, const void* bases_dev, const void* scalars_dev, uint64_t n, bool mont, void* out_dev) {
+static int32_t msm_run_t(Ctx* c, const void* bases_dev, const void* scalars_dev, uint64_t n, bool mont, void* out_dev, void* wins_ext) {
     using Fr = typename Curve::Fr;
     using Pt = XYZZ<F>;
     if (n >= (1ull << 31)) return fail(c, B2S_ERR_INVALID_ARG, "msm: n = %llu exceeds 2^31 - 1", (unsigned long long)n);
@@ -409,7 +409,9 @@ static int32_t msm_run_t(Ctx* c, const void* bases_dev, const void* scalars_dev,
     B2S_TRY(partials.alloc(c, (size_t)sh.max_tasks * sizeof(Pt)));
     const uint32_t segs_per_win = (sh.B + MSM_SEG - 1) / MSM_SEG;
     B2S_TRY(segs.alloc(c, (size_t)segs_per_win * sh.nwin * sizeof(Pt)));
-    B2S_TRY(wins.alloc(c, (size_t)sh.nwin * sizeof(Pt)));
+    if (sh.nwin > 64) wins_ext = nullptr;   // caller scratch holds 64 window sums; tiny windows take the in-stream path
+    if (!wins_ext) B2S_TRY(wins.alloc(c, (size_t)sh.nwin * sizeof(Pt)));
+    Pt* wins_p = wins_ext ? reinterpret_cast<Pt*>(wins_ext) : wins.as<Pt>();
 
     B2S_LAUNCH(c, msm_count_kernel<Fr>, cdiv(n, 256), 256, 0, scalars, n, mont, sh, counts);
     B2S_LAUNCH(c, msm_scan_tiles_kernel, ntiles, SCAN_THREADS, 0, counts, sh, tiles.as<Scan3>());
@@ -435,17 +437,33 @@ static int32_t msm_run_t(Ctx* c, const void* bases_dev, const void* scalars_dev,
                partials.as<Pt>(), heavy_tmp.as<Pt>(), bucket_acc.as<Pt>());
     B2S_LAUNCH(c, msm_bucket_segments_kernel<F>, cdiv((uint64_t)segs_per_win * sh.nwin, 128), 128, 0,
                bucket_acc.as<Pt>(), sh, MSM_SEG, segs.as<Pt>());
-    B2S_LAUNCH(c, msm_window_sum_kernel<F>, sh.nwin, MSM_RED_THREADS, red_smem, segs.as<Pt>(), segs_per_win, wins.as<Pt>());
-    B2S_TRY(msm_horner(c, is_g1 ? 1 : 2, wins.p, sh, out));
+    B2S_LAUNCH(c, msm_window_sum_kernel<F>, sh.nwin, MSM_RED_THREADS, red_smem, segs.as<Pt>(), segs_per_win, wins_p);
+    if (!wins_ext) {
+        B2S_TRY(msm_horner(c, c->stream, is_g1 ? 1 : 2, wins_p, sh, out));
+    } else {
+        // tail on the aux stream: it only needs the window sums, the main stream goes on with the next MSM
+        B2S_CUDA(c, cudaEventRecord(c->ev_tail, c->stream));
+        B2S_CUDA(c, cudaStreamWaitEvent(c->aux, c->ev_tail, 0));
+        B2S_TRY(msm_horner(c, c->aux, is_g1 ? 1 : 2, wins_p, sh, out));
+        c->aux_pending = true;
+    }
+    return B2S_OK;
+}
+
+int32_t msm_join_tails(Ctx* c) {
+    if (!c->aux_pending) return B2S_OK;
+    B2S_CUDA(c, cudaEventRecord(c->ev_done, c->aux));
+    B2S_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_done, 0));
+    c->aux_pending = false;
     return B2S_OK;
 }
 
 int32_t msm_run(Ctx* c, int group, const void* bases_dev, const void* scalars_dev, uint64_t n, bool scalars_mont,
-                void* out_xyzz_dev) {
+                void* out_xyzz_dev, void* wins_ext) {
     return dispatch_curve(c, [&](auto curve) {
         using C = decltype(curve);
-        if (group == 1) return msm_run_t<C, typename C::Fq>(c, bases_dev, scalars_dev, n, scalars_mont, out_xyzz_dev);
-        return msm_run_t<C, typename C::Fq2>(c, bases_dev, scalars_dev, n, scalars_mont, out_xyzz_dev);
+        if (group == 1) return msm_run_t<C, typename C::Fq>(c, bases_dev, scalars_dev, n, scalars_mont, out_xyzz_dev, wins_ext);
+        return msm_run_t<C, typename C::Fq2>(c, bases_dev, scalars_dev, n, scalars_mont, out_xyzz_dev, wins_ext);
     });
 }
 

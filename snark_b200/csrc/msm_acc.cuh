@@ -114,10 +114,10 @@ __global__ void msm_horner_kernel(const XYZZ<F>* __restrict__ win, MsmShape sh, 
 // launches compiled with the multiplication inlined: msm_acc_g1.cu (G1) and msm_acc_g2.cu (G2)
 int32_t msm_accumulate_g2(Ctx* c, const void* bases, const uint32_t* sorted, const uint32_t* offsets,
                           const uint32_t* task_off, MsmShape sh, void* bucket_acc, void* partials);
-int32_t msm_horner_g1(Ctx* c, const void* wins, MsmShape sh, void* out);
-int32_t msm_horner_g2(Ctx* c, const void* wins, MsmShape sh, void* out);
-inline int32_t msm_horner(Ctx* c, int group, const void* wins, MsmShape sh, void* out) {
-    return group == 1 ? msm_horner_g1(c, wins, sh, out) : msm_horner_g2(c, wins, sh, out);
+int32_t msm_horner_g1(Ctx* c, cudaStream_t st, const void* wins, MsmShape sh, void* out);
+int32_t msm_horner_g2(Ctx* c, cudaStream_t st, const void* wins, MsmShape sh, void* out);
+inline int32_t msm_horner(Ctx* c, cudaStream_t st, int group, const void* wins, MsmShape sh, void* out) {
+    return group == 1 ? msm_horner_g1(c, st, wins, sh, out) : msm_horner_g2(c, st, wins, sh, out);
 }
 // G1 accumulate for the ctx's curve (msm_acc_g1.cu)
 int32_t msm_accumulate_g1(Ctx* c, const void* bases, const uint32_t* sorted, const uint32_t* offsets,

@@ -20,6 +20,7 @@ struct b2s_pk {
     b2s::DevBuf consts_g1;            // alpha_g1, beta_g1, delta_g1 (affine)
     b2s::DevBuf consts_g2;            // beta_g2, delta_g2 (affine)
     b2s::DevBuf a_query, b_g1_query, b_g2_query, h_query, l_query;
+    uint32_t a_ext = 0, b1_ext = 0, b2_ext = 0;   // 2 when this shard owns the end of the range (extra delta pairs)
     uint64_t a_off = 0, a_len = 0, b1_off = 0, b1_len = 0, b2_off = 0, b2_len = 0, h_off = 0, h_len = 0, l_off = 0, l_len = 0;
 };
 
@@ -33,7 +34,8 @@ int32_t witness_map_run(Ctx* c, const b2s_r1cs* m, const void* z_dev, void* h_de
 int32_t pk_upload(Ctx* c, const b2s_pk_desc* d, int32_t mem, b2s_pk** out);
 // z either as two host pieces (z_dev == nullptr) or as one device array
 int32_t groth16_shard(Ctx* c, const b2s_pk* pk, const b2s_r1cs* m, const void* z_inst_host, const void* z_wit_host,
-                      const void* z_dev, void* g1_partials_dev /*4 xyzz*/, void* g2_partial_dev /*1 xyzz*/);
+                      const void* z_dev, const void* r_host, const void* s_host, void* g1_partials_dev /*4 xyzz*/,
+                      void* g2_partial_dev /*1 xyzz*/);
 int32_t groth16_finish(Ctx* c, const b2s_pk* pk, const void* g1_partials_dev, const void* g2_partials_dev, uint32_t n_shards,
                        const void* r_host, const void* s_host, void* out_a, void* out_b, void* out_c);
 }  // namespace b2s

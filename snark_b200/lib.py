@@ -61,9 +61,9 @@ SIGNATURES = {
     "b2s_pk_upload": (c_int32, [c_void_p, POINTER(PkDesc), c_int32, POINTER(c_void_p)]),
     "b2s_pk_free": (None, [c_void_p, c_void_p]),
     "b2s_groth16_prove": (c_int32, [c_void_p] * 10),
-    "b2s_groth16_prove_shard": (c_int32, [c_void_p] * 7),
+    "b2s_groth16_prove_shard": (c_int32, [c_void_p] * 9),
     "b2s_groth16_prove_resident": (c_int32, [c_void_p] * 9),
-    "b2s_groth16_prove_shard_resident": (c_int32, [c_void_p] * 6),
+    "b2s_groth16_prove_shard_resident": (c_int32, [c_void_p] * 8),
     "b2s_profile_enable": (c_int32, [c_void_p, c_int32]),
     "b2s_profile_report": (c_int32, [c_void_p, c_char_p, c_uint64]),
     "b2s_groth16_finish": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_uint32, c_void_p, c_void_p, c_void_p,
@@ -266,10 +266,11 @@ class Backend:
                                                      a.ctypes.data, b.ctypes.data, c.ctypes.data))
         return a, b, c
 
-    def groth16_prove_shard_resident(self, pk, m, z_dev):
+    def groth16_prove_shard_resident(self, pk, m, z_dev, r, s):
         g1 = np.zeros(4 * self.g1x_bytes // 4, dtype=np.uint32)
         g2 = np.zeros(self.g2x_bytes // 4, dtype=np.uint32)
-        self._ck(self.lib.b2s_groth16_prove_shard_resident(self.h, pk, m, _ptr(z_dev)[0], g1.ctypes.data, g2.ctypes.data))
+        self._ck(self.lib.b2s_groth16_prove_shard_resident(self.h, pk, m, _ptr(z_dev)[0], r.ctypes.data, s.ctypes.data,
+                                                           g1.ctypes.data, g2.ctypes.data))
         return g1, g2
 
     def profile(self, on=True):
@@ -285,11 +286,11 @@ class Backend:
             out[name] = (int(cnt), float(ms))
         return out
 
-    def groth16_prove_shard(self, pk, m, z_inst, z_wit):
+    def groth16_prove_shard(self, pk, m, z_inst, z_wit, r, s):
         g1 = np.zeros(4 * self.g1x_bytes // 4, dtype=np.uint32)
         g2 = np.zeros(self.g2x_bytes // 4, dtype=np.uint32)
-        self._ck(self.lib.b2s_groth16_prove_shard(self.h, pk, m, _ptr(z_inst)[0], _ptr(z_wit)[0], g1.ctypes.data,
-                                                  g2.ctypes.data))
+        self._ck(self.lib.b2s_groth16_prove_shard(self.h, pk, m, _ptr(z_inst)[0], _ptr(z_wit)[0], r.ctypes.data, s.ctypes.data,
+                                                  g1.ctypes.data, g2.ctypes.data))
         return g1, g2
 
     def groth16_finish(self, pk, g1_partials, g2_partials, n_shards, r, s):

@@ -145,7 +145,7 @@ def test_groth16_shards_join(be):
     for i in range(2):
         h = be.pk_upload(shard(i, 2))
         handles.append(h)
-        g1, g2 = be.groth16_prove_shard(h, m, pack_fr(curve, inst), pack_fr(curve, wit))
+        g1, g2 = be.groth16_prove_shard(h, m, pack_fr(curve, inst), pack_fr(curve, wit), pack_fr(curve, [rr]), pack_fr(curve, [ss]))
         parts1.append(g1)
         parts2.append(g2)
     a, b, c = be.groth16_finish(handles[0], np.concatenate(parts1), np.concatenate(parts2), 2, pack_fr(curve, [rr]), pack_fr(curve, [ss]))
