@@ -1,0 +1,60 @@
+"""The C++ host mirror of the ark-relations / ark-snark API (snark_b200/host/*.hpp).
+
+CPU part: tests/native/host_relations_test.cpp re-runs the reference's own unit tests (golden circuit2
+matrices, satisfiability, variable ordering, LC quirks) against the mirror.  GPU part: the mirror's
+Groth16 (`circuit_specific_setup` + `prove`, every group operation through the C ABI) must give the very
+proof the Python oracle computes for the same trapdoor and (r, s)."""
+import os
+import subprocess
+
+import pytest
+
+from oracle import groth16 as og
+from oracle import r1cs as orc
+from oracle.ec import groups
+from oracle.params import BLS12_381, BN254
+from tests.util import unpack_points
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+EXE = os.path.join(ROOT, "tests", "native", "host_relations_test")
+SRC = os.path.join(ROOT, "tests", "native", "host_relations_test.cpp")
+
+
+def build():
+    deps = [SRC] + [os.path.join(ROOT, "snark_b200", "host", f) for f in ("ark_relations.hpp", "ark_snark.hpp")]
+    if not os.path.exists(EXE) or any(os.path.getmtime(d) > os.path.getmtime(EXE) for d in deps):
+        subprocess.check_call(["g++", "-O1", "-std=c++17", "-o", EXE, SRC, "-L", os.path.join(ROOT, "snark_b200"), "-lb200snark",
+                               "-Wl,-rpath," + os.path.join(ROOT, "snark_b200")])
+    return EXE
+
+
+def test_reference_unit_tests_against_cpp_mirror():
+    out = subprocess.run([build(), "cpu"], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "bls12_381 cpu tests: ok" in out.stdout and "bn254 cpu tests: ok" in out.stdout and "FAIL" not in out.stdout
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("cid,circuit", [(0, "circuit2"), (0, "dummy"), (1, "circuit2"), (1, "dummy")])
+def test_cpp_groth16_matches_oracle(cid, circuit):
+    import numpy as np
+
+    curve = [BLS12_381, BN254][cid]
+    td_vals = [1234567, 31337, 271828, 314159, 161803]
+    rr, ss = 99991, 77773
+    out = subprocess.run([build(), "gpu", str(cid), circuit] + [str(v) for v in td_vals + [rr, ss]], capture_output=True, text=True,
+                         timeout=300)
+    assert out.returncode == 0, out.stdout + out.stderr
+    got = {}
+    for line in out.stdout.splitlines():
+        tag, *words = line.split()
+        got[tag] = np.array([int(w, 16) for w in words], dtype=np.uint32)
+    cs = orc.circuit2(curve, 1, 1, 2) if circuit == "circuit2" else orc.dummy_circuit(curve, 3, 5, 16, 16)
+    cs.finalize()
+    mats, inst, wit = cs.to_matrices(), cs.instance_assignment, cs.witness_assignment
+    pk = og.setup(curve, mats, len(inst), len(wit), og.Trapdoor(*td_vals))
+    A, B, C, h = og.prove(pk, mats, inst, wit, rr, ss)
+    assert og.check_in_exponent(pk, (A, B, C), inst, wit, h, rr, ss)
+    assert unpack_points(curve, 1, got["alpha_g1"])[0] == pk.alpha_g1
+    assert unpack_points(curve, 1, got["h_query0"])[0] == pk.h_query[0]
+    assert (unpack_points(curve, 1, got["A"])[0], unpack_points(curve, 2, got["B"])[0], unpack_points(curve, 1, got["C"])[0]) == (A, B, C)
