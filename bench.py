@@ -178,8 +178,9 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return  # rank 0 alone runs the CPU arm
-    cores = os.cpu_count() or 1
-    log_s = args.ref_log_n or (20 if cores >= 64 else 16)
+    from oracle import cnative
+    cores = cnative.threads_default()
+    log_s = args.ref_log_n or (20 if cores >= 16 else 16)
     log_s = min(log_s, args.log_n)
     sec, threads = cpu_prove_sample(log_s, args.steps, args.warmup)
     scale = (1 << log_s) / (1 << args.log_n)          # work is ~linear in the domain size (MSM-dominated)
@@ -371,8 +372,9 @@ def run_b200(args):
     if world == 1 and not args.no_extras:
         out["extras"] = extras(be, torch, dev, ext, peak)
     if world == 1 and not args.no_cpu:
-        cores = os.cpu_count() or 1
-        log_s = min(args.ref_log_n or (20 if cores >= 64 else 16), args.log_n)
+        from oracle import cnative
+        cores = cnative.threads_default()
+        log_s = min(args.ref_log_n or (20 if cores >= 16 else 16), args.log_n)
         sec, threads = cpu_prove_sample(log_s, 1, 0)
         scale = (1 << log_s) / (1 << args.log_n)
         out["cpu_baseline"] = {"value": scale / sec, "unit": "proofs/s", "cores": threads, "kind": "port",

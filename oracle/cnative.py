@@ -32,7 +32,16 @@ def load(build=True):
 
 
 def threads_default():
-    return load().orc_threads_default()
+    """Host threads the CPU baseline may actually use: min(visible CPUs, scheduler affinity, cgroup CPU quota).
+    (The GPU boxes show 128 CPUs but cap the container at 16 via cpu.max; oversubscribing is slower.)"""
+    n = min(load().orc_threads_default(), len(os.sched_getaffinity(0)))
+    try:
+        quota, period = open("/sys/fs/cgroup/cpu.max").read().split()
+        if quota != "max":
+            n = max(1, min(n, int(quota) // int(period)))
+    except (OSError, ValueError):
+        pass
+    return n
 
 
 def _p(a):
