@@ -23,7 +23,7 @@
 // Roofline: per (point, scalar) the algorithmic HBM traffic is 96+32 B (G1 BLS12-381), but each point
 // costs ceil(255/c) mixed additions of ~10 Fq multiplications = ~3000 wide IMADs; the kernel is
 // bound by the fma pipe by two orders of magnitude over HBM (DESIGN.md has the numbers).
-#include "msm_acc.cuh"
+#include "msm_affine.cuh"
 
 namespace b2s {
 
@@ -419,8 +419,42 @@ static int32_t msm_run_t(Ctx* c, const void* bases_dev, const void* scalars_dev,
     B2S_LAUNCH(c, msm_scan_apply_kernel, ntiles, SCAN_THREADS, 0, counts, sh, tiles.as<Scan3>(), offsets, task_off, heavy);
     B2S_LAUNCH(c, msm_scatter_kernel<Fr>, cdiv(n, 256), 256, 0, scalars, n, mont, sh, offsets, cursor, sorted.as<uint32_t>());
     constexpr bool is_g1 = sizeof(F) == sizeof(typename Curve::Fq);
-    if (is_g1) B2S_TRY(msm_accumulate_g1(c, bases, sorted.as<uint32_t>(), offsets, task_off, sh, bucket_acc.p, partials.p));
-    else B2S_TRY(msm_accumulate_g2(c, bases, sorted.as<uint32_t>(), offsets, task_off, sh, bucket_acc.p, partials.p));
+    // optional batched-affine halving rounds (msm_affine.cuh); afterwards the points are already in bucket order
+    const uint32_t ba_rounds = env_u32("B2S_MSM_AFFINE_ROUNDS", 0);
+    const uint32_t ba_k = max(1u, env_u32("B2S_MSM_AFFINE_K", 256));
+    const void* acc_bases = bases;
+    const uint32_t* acc_sorted = sorted.as<uint32_t>();
+    const uint32_t* acc_offsets = offsets;
+    DevBuf ba_ints, ba_out[2], ba_prefix;
+    if (ba_rounds) {
+        B2S_TRY(ba_ints.alloc(c, ((size_t)2 * sh.G + 1) * sizeof(uint32_t)));
+        uint32_t* cnt[2] = {counts, ba_ints.as<uint32_t>()};
+        uint32_t* off[2] = {offsets, ba_ints.as<uint32_t>() + sh.G};
+        uint64_t t_in = (uint64_t)sh.nwin * n;
+        int cur = 0;
+        const void* prev = nullptr;
+        for (uint32_t r = 0; r < ba_rounds; r++) {
+            const int nxt = cur ^ 1;
+            const uint64_t out_bound = (t_in + sh.G) / 2 + 1;
+            B2S_LAUNCH(c, msm_ba_halve_kernel, cdiv(sh.G, 256), 256, 0, cnt[cur], sh.G, cnt[nxt]);
+            B2S_LAUNCH(c, msm_scan_tiles_kernel, ntiles, SCAN_THREADS, 0, cnt[nxt], sh, tiles.as<Scan3>());
+            B2S_LAUNCH(c, msm_scan_spine_kernel, 1, 1024, 0, tiles.as<Scan3>(), ntiles, sh, off[nxt], task_off, heavy);
+            B2S_LAUNCH(c, msm_scan_apply_kernel, ntiles, SCAN_THREADS, 0, cnt[nxt], sh, tiles.as<Scan3>(), off[nxt], task_off, heavy);
+            B2S_TRY(ba_out[nxt].alloc(c, out_bound * sizeof(Affine<F>)));
+            B2S_TRY(ba_prefix.alloc(c, out_bound * sizeof(F)));
+            if (is_g1) B2S_TRY(msm_ba_round_g1(c, r == 0, bases, sorted.as<uint32_t>(), prev, off[cur], off[nxt], sh.G, ba_k, out_bound, ba_prefix.p, ba_out[nxt].p));
+            else B2S_TRY(msm_ba_round_g2(c, r == 0, bases, sorted.as<uint32_t>(), prev, off[cur], off[nxt], sh.G, ba_k, out_bound, ba_prefix.p, ba_out[nxt].p));
+            prev = ba_out[nxt].p;
+            ba_out[cur].release();
+            t_in = out_bound;
+            cur = nxt;
+        }
+        acc_bases = prev;
+        acc_sorted = nullptr;
+        acc_offsets = off[cur];
+    }
+    if (is_g1) B2S_TRY(msm_accumulate_g1(c, acc_bases, acc_sorted, acc_offsets, task_off, sh, bucket_acc.p, partials.p));
+    else B2S_TRY(msm_accumulate_g2(c, acc_bases, acc_sorted, acc_offsets, task_off, sh, bucket_acc.p, partials.p));
     const size_t red_smem = (size_t)MSM_RED_THREADS * sizeof(Pt);
     static bool attr_done[2][2] = {{false, false}, {false, false}};
     constexpr int gi = sizeof(F) == sizeof(typename Curve::Fq) ? 0 : 1;

@@ -2,7 +2,7 @@
 // with the multiplication inlined: 252 registers, no spills, two CTAs of 128 threads per SM -- which
 // the micro-benchmark shows is enough warps to keep the fmaheavy pipe full (profiles/r01_microbench.txt).
 #define B2S_INLINE_MUL 1
-#include "msm_acc.cuh"
+#include "msm_affine.cuh"
 
 namespace b2s {
 
@@ -22,6 +22,14 @@ int32_t msm_horner_g2(Ctx* c, cudaStream_t st, const void* wins, MsmShape sh, vo
         using F = typename decltype(curve)::Fq2;
         B2S_LAUNCH_SN(c, st, "msm_horner_g2", msm_horner_kernel<F>, 1, 32, 0, reinterpret_cast<const XYZZ<F>*>(wins), sh, reinterpret_cast<XYZZ<F>*>(out));
         return (int32_t)B2S_OK;
+    });
+}
+
+int32_t msm_ba_round_g2(Ctx* c, bool first, const void* bases, const uint32_t* sorted, const void* prev, const uint32_t* in_off,
+                        const uint32_t* out_off, uint32_t G, uint32_t K, uint64_t out_bound, void* prefix, void* out) {
+    return dispatch_curve(c, [&](auto curve) {
+        using F = typename decltype(curve)::Fq2;
+        return msm_ba_round_launch<F>(c, "msm_ba_round_g2", first, bases, sorted, prev, in_off, out_off, G, K, out_bound, prefix, out);
     });
 }
 
