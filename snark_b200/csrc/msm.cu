@@ -78,6 +78,51 @@ __global__ void msm_count_kernel(const Fr* __restrict__ scalars, uint64_t n, boo
     }
 }
 
+// Buckets ordered by decreasing size (counting sort on min(count, SIZE_BINS - 1)): task ranks follow this order,
+// so the 32 tasks a warp executes in lockstep have (nearly) the same length.  With uniformly random scalars the
+// bucket sizes are Poisson; in natural order a warp waits for its longest bucket (+37 % at a mean of 32 points).
+static constexpr uint32_t SIZE_BINS = 4096;
+
+__global__ void msm_size_hist_kernel(const uint32_t* __restrict__ counts, uint32_t G, uint32_t* __restrict__ hist) {
+    const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= G) return;
+    const unsigned active = __activemask();
+    const uint32_t key = SIZE_BINS - 1 - min(counts[g], SIZE_BINS - 1);
+    const unsigned peers = __match_any_sync(active, key);
+    if ((threadIdx.x & 31) == (unsigned)(__ffs(peers) - 1)) atomicAdd(&hist[key], (uint32_t)__popc(peers));
+}
+// hist -> exclusive offsets in place in `binoff`; clears hist for reuse as the scatter cursor
+__global__ void msm_size_scan_kernel(uint32_t* __restrict__ hist, uint32_t* __restrict__ binoff) {
+    __shared__ uint32_t part[1024];
+    const uint32_t per = SIZE_BINS / 1024;
+    uint32_t local[per], sum = 0;
+    for (uint32_t k = 0; k < per; k++) { local[k] = hist[threadIdx.x * per + k]; sum += local[k]; }
+    part[threadIdx.x] = sum;
+    __syncthreads();
+    for (uint32_t d = 1; d < 1024; d <<= 1) {
+        uint32_t a = threadIdx.x >= d ? part[threadIdx.x - d] : 0;
+        __syncthreads();
+        part[threadIdx.x] += a;
+        __syncthreads();
+    }
+    uint32_t run = part[threadIdx.x] - sum;
+    for (uint32_t k = 0; k < per; k++) { binoff[threadIdx.x * per + k] = run; run += local[k]; hist[threadIdx.x * per + k] = 0; }
+}
+__global__ void msm_size_scatter_kernel(const uint32_t* __restrict__ counts, uint32_t G, const uint32_t* __restrict__ binoff,
+                                        uint32_t* __restrict__ cursor, uint32_t* __restrict__ perm) {
+    const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= G) return;
+    const unsigned active = __activemask();
+    const unsigned lane = threadIdx.x & 31;
+    const uint32_t key = SIZE_BINS - 1 - min(counts[g], SIZE_BINS - 1);
+    const unsigned peers = __match_any_sync(active, key);
+    const unsigned leader = (unsigned)(__ffs(peers) - 1);
+    uint32_t base = 0;
+    if (lane == leader) base = atomicAdd(&cursor[key], (uint32_t)__popc(peers));
+    base = __shfl_sync(peers, base, leader);
+    perm[binoff[key] + base + __popc(peers & ((1u << lane) - 1u))] = g;
+}
+
 // Exclusive scans over the G bucket counts, in three kernels (tile sums -> scan of tile sums -> apply):
 //   offsets[g]  = number of points in buckets < g        (position in the sorted index array)
 //   task_off[g] = number of tasks in buckets < g         (a bucket of s points has ceil(s / L) tasks)
@@ -118,14 +163,15 @@ __device__ __forceinline__ Scan3 block_scan(Scan3 v, Scan3* total) {
 }
 
 __global__ void __launch_bounds__(SCAN_THREADS)
-msm_scan_tiles_kernel(const uint32_t* __restrict__ counts, MsmShape sh, Scan3* __restrict__ tile_sums) {
+msm_scan_tiles_kernel(const uint32_t* __restrict__ counts, const uint32_t* __restrict__ perm, MsmShape sh,
+                      Scan3* __restrict__ tile_sums) {
     const uint32_t base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_PER_THREAD;
     Scan3 v{0, 0, 0};
 #pragma unroll
     for (int k = 0; k < SCAN_PER_THREAD; k++) {
         const uint32_t g = base + k;
         if (g < sh.G) {
-            const uint32_t s = counts[g], t = (s + sh.L - 1) / sh.L;
+            const uint32_t s = counts[perm ? perm[g] : g], t = (s + sh.L - 1) / sh.L;
             v = v + Scan3{s, t, t > 1 ? 1u : 0u};
         }
     }
@@ -151,14 +197,15 @@ msm_scan_spine_kernel(Scan3* __restrict__ tile_sums, uint32_t ntiles, MsmShape s
         run = run + t;
     }
     if (threadIdx.x == 0) {
-        offsets[sh.G] = total.pts;
+        if (offsets) offsets[sh.G] = total.pts;
         task_off[sh.G] = total.tsk;
         heavy[0] = total.hvy;
     }
 }
 
 __global__ void __launch_bounds__(SCAN_THREADS)
-msm_scan_apply_kernel(const uint32_t* __restrict__ counts, MsmShape sh, const Scan3* __restrict__ tile_sums,
+msm_scan_apply_kernel(const uint32_t* __restrict__ counts, const uint32_t* __restrict__ perm, MsmShape sh,
+                      const Scan3* __restrict__ tile_sums,
                       uint32_t* __restrict__ offsets, uint32_t* __restrict__ task_off, uint32_t* __restrict__ heavy) {
     const uint32_t base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_PER_THREAD;
     uint32_t s[SCAN_PER_THREAD], t[SCAN_PER_THREAD];
@@ -166,7 +213,7 @@ msm_scan_apply_kernel(const uint32_t* __restrict__ counts, MsmShape sh, const Sc
 #pragma unroll
     for (int k = 0; k < SCAN_PER_THREAD; k++) {
         const uint32_t g = base + k;
-        s[k] = g < sh.G ? counts[g] : 0u;
+        s[k] = g < sh.G ? counts[perm ? perm[g] : g] : 0u;
         t[k] = (s[k] + sh.L - 1) / sh.L;
         v = v + Scan3{s[k], t[k], t[k] > 1 ? 1u : 0u};
     }
@@ -178,7 +225,7 @@ msm_scan_apply_kernel(const uint32_t* __restrict__ counts, MsmShape sh, const Sc
     for (int k = 0; k < SCAN_PER_THREAD; k++) {
         const uint32_t g = base + k;
         if (g < sh.G) {
-            offsets[g] = run.pts;
+            if (offsets) offsets[g] = run.pts;
             task_off[g] = run.tsk;
             if (t[k] > 1) heavy[1 + run.hvy] = g;
             run = run + Scan3{s[k], t[k], t[k] > 1 ? 1u : 0u};
@@ -242,7 +289,7 @@ static constexpr uint32_t HEAVY_BIG = 16 * HEAVY_SPLIT;
 template <class F>
 __global__ void __launch_bounds__(MSM_RED_THREADS)
 msm_reduce_heavy_stage1_kernel(const uint32_t* __restrict__ heavy, const uint32_t* __restrict__ task_off,
-                               const XYZZ<F>* __restrict__ partials, XYZZ<F>* __restrict__ tmp) {
+                               const XYZZ<F>* __restrict__ partials, XYZZ<F>* __restrict__ tmp) {   // heavy[] holds ranks
     extern __shared__ uint4 smem_raw[];
     XYZZ<F>* smem = reinterpret_cast<XYZZ<F>*>(smem_raw);
     const uint32_t nitems = heavy[0] * HEAVY_SPLIT;
@@ -259,14 +306,15 @@ msm_reduce_heavy_stage1_kernel(const uint32_t* __restrict__ heavy, const uint32_
 
 template <class F>
 __global__ void __launch_bounds__(MSM_RED_THREADS)
-msm_reduce_heavy_kernel(const uint32_t* __restrict__ heavy, const uint32_t* __restrict__ task_off,
+msm_reduce_heavy_kernel(const uint32_t* __restrict__ heavy, const uint32_t* __restrict__ task_off, const uint32_t* __restrict__ perm,
                         const XYZZ<F>* __restrict__ partials, const XYZZ<F>* __restrict__ tmp, XYZZ<F>* __restrict__ bucket_acc) {
     extern __shared__ uint4 smem_raw[];
     XYZZ<F>* smem = reinterpret_cast<XYZZ<F>*>(smem_raw);
     const uint32_t nheavy = heavy[0];
     for (uint32_t h = blockIdx.x; h < nheavy; h += gridDim.x) {
-        const uint32_t g = heavy[1 + h];
-        const uint32_t t0 = task_off[g], cnt = task_off[g + 1] - t0;
+        const uint32_t rk = heavy[1 + h];
+        const uint32_t g = perm ? perm[rk] : rk;
+        const uint32_t t0 = task_off[rk], cnt = task_off[rk + 1] - t0;
         XYZZ<F> s = cnt < HEAVY_BIG ? cta_sum(partials + t0, cnt, smem) : cta_sum(tmp + t0 / HEAVY_SPLIT, HEAVY_SPLIT, smem);
         if (threadIdx.x == 0) st_struct(bucket_acc + g, s);
         __syncthreads();
@@ -414,9 +462,10 @@ static int32_t msm_run_t(Ctx* c, const void* bases_dev, const void* scalars_dev,
     Pt* wins_p = wins_ext ? reinterpret_cast<Pt*>(wins_ext) : wins.as<Pt>();
 
     B2S_LAUNCH(c, msm_count_kernel<Fr>, cdiv(n, 256), 256, 0, scalars, n, mont, sh, counts);
-    B2S_LAUNCH(c, msm_scan_tiles_kernel, ntiles, SCAN_THREADS, 0, counts, sh, tiles.as<Scan3>());
+    const uint32_t* no_perm = nullptr;
+    B2S_LAUNCH(c, msm_scan_tiles_kernel, ntiles, SCAN_THREADS, 0, counts, no_perm, sh, tiles.as<Scan3>());
     B2S_LAUNCH(c, msm_scan_spine_kernel, 1, 1024, 0, tiles.as<Scan3>(), ntiles, sh, offsets, task_off, heavy);
-    B2S_LAUNCH(c, msm_scan_apply_kernel, ntiles, SCAN_THREADS, 0, counts, sh, tiles.as<Scan3>(), offsets, task_off, heavy);
+    B2S_LAUNCH(c, msm_scan_apply_kernel, ntiles, SCAN_THREADS, 0, counts, no_perm, sh, tiles.as<Scan3>(), offsets, task_off, heavy);
     B2S_LAUNCH(c, msm_scatter_kernel<Fr>, cdiv(n, 256), 256, 0, scalars, n, mont, sh, offsets, cursor, sorted.as<uint32_t>());
     constexpr bool is_g1 = sizeof(F) == sizeof(typename Curve::Fq);
     // optional batched-affine halving rounds (msm_affine.cuh); afterwards the points are already in bucket order
@@ -437,9 +486,9 @@ static int32_t msm_run_t(Ctx* c, const void* bases_dev, const void* scalars_dev,
             const int nxt = cur ^ 1;
             const uint64_t out_bound = (t_in + sh.G) / 2 + 1;
             B2S_LAUNCH(c, msm_ba_halve_kernel, cdiv(sh.G, 256), 256, 0, cnt[cur], sh.G, cnt[nxt]);
-            B2S_LAUNCH(c, msm_scan_tiles_kernel, ntiles, SCAN_THREADS, 0, cnt[nxt], sh, tiles.as<Scan3>());
+            B2S_LAUNCH(c, msm_scan_tiles_kernel, ntiles, SCAN_THREADS, 0, cnt[nxt], no_perm, sh, tiles.as<Scan3>());
             B2S_LAUNCH(c, msm_scan_spine_kernel, 1, 1024, 0, tiles.as<Scan3>(), ntiles, sh, off[nxt], task_off, heavy);
-            B2S_LAUNCH(c, msm_scan_apply_kernel, ntiles, SCAN_THREADS, 0, cnt[nxt], sh, tiles.as<Scan3>(), off[nxt], task_off, heavy);
+            B2S_LAUNCH(c, msm_scan_apply_kernel, ntiles, SCAN_THREADS, 0, cnt[nxt], no_perm, sh, tiles.as<Scan3>(), off[nxt], task_off, heavy);
             B2S_TRY(ba_out[nxt].alloc(c, out_bound * sizeof(Affine<F>)));
             B2S_TRY(ba_prefix.alloc(c, out_bound * sizeof(F)));
             if (is_g1) B2S_TRY(msm_ba_round_g1(c, r == 0, bases, sorted.as<uint32_t>(), prev, off[cur], off[nxt], sh.G, ba_k, out_bound, ba_prefix.p, ba_out[nxt].p));
@@ -453,8 +502,26 @@ static int32_t msm_run_t(Ctx* c, const void* bases_dev, const void* scalars_dev,
         acc_sorted = nullptr;
         acc_offsets = off[cur];
     }
-    if (is_g1) B2S_TRY(msm_accumulate_g1(c, acc_bases, acc_sorted, acc_offsets, task_off, sh, bucket_acc.p, partials.p));
-    else B2S_TRY(msm_accumulate_g2(c, acc_bases, acc_sorted, acc_offsets, task_off, sh, bucket_acc.p, partials.p));
+    // task ranks by decreasing bucket size (skipped after affine rounds, which leave the natural order)
+    const uint32_t* perm = nullptr;
+    DevBuf perm_buf;
+    if (!ba_rounds && env_u32("B2S_MSM_SIZE_SORT", 1)) {
+        B2S_TRY(perm_buf.alloc(c, ((size_t)sh.G + 2 * SIZE_BINS) * sizeof(uint32_t)));
+        uint32_t* pm = perm_buf.as<uint32_t>();
+        uint32_t* hist = pm + sh.G;
+        uint32_t* binoff = hist + SIZE_BINS;
+        uint32_t* none = nullptr;
+        B2S_CUDA(c, cudaMemsetAsync(hist, 0, SIZE_BINS * sizeof(uint32_t), c->stream));
+        B2S_LAUNCH(c, msm_size_hist_kernel, cdiv(sh.G, 256), 256, 0, counts, sh.G, hist);
+        B2S_LAUNCH(c, msm_size_scan_kernel, 1, 1024, 0, hist, binoff);
+        B2S_LAUNCH(c, msm_size_scatter_kernel, cdiv(sh.G, 256), 256, 0, counts, sh.G, binoff, hist, pm);
+        B2S_LAUNCH(c, msm_scan_tiles_kernel, ntiles, SCAN_THREADS, 0, counts, (const uint32_t*)pm, sh, tiles.as<Scan3>());
+        B2S_LAUNCH(c, msm_scan_spine_kernel, 1, 1024, 0, tiles.as<Scan3>(), ntiles, sh, none, task_off, heavy);
+        B2S_LAUNCH(c, msm_scan_apply_kernel, ntiles, SCAN_THREADS, 0, counts, (const uint32_t*)pm, sh, tiles.as<Scan3>(), none, task_off, heavy);
+        perm = pm;
+    }
+    if (is_g1) B2S_TRY(msm_accumulate_g1(c, acc_bases, acc_sorted, acc_offsets, task_off, perm, sh, bucket_acc.p, partials.p));
+    else B2S_TRY(msm_accumulate_g2(c, acc_bases, acc_sorted, acc_offsets, task_off, perm, sh, bucket_acc.p, partials.p));
     const size_t red_smem = (size_t)MSM_RED_THREADS * sizeof(Pt);
     static bool attr_done[2][2] = {{false, false}, {false, false}};
     constexpr int gi = sizeof(F) == sizeof(typename Curve::Fq) ? 0 : 1;
@@ -467,7 +534,7 @@ static int32_t msm_run_t(Ctx* c, const void* bases_dev, const void* scalars_dev,
     }
     B2S_LAUNCH(c, msm_reduce_heavy_stage1_kernel<F>, 4 * c->sm_count, MSM_RED_THREADS, red_smem, heavy, task_off,
                partials.as<Pt>(), heavy_tmp.as<Pt>());
-    B2S_LAUNCH(c, msm_reduce_heavy_kernel<F>, 2 * c->sm_count, MSM_RED_THREADS, red_smem, heavy, task_off,
+    B2S_LAUNCH(c, msm_reduce_heavy_kernel<F>, 2 * c->sm_count, MSM_RED_THREADS, red_smem, heavy, task_off, perm,
                partials.as<Pt>(), heavy_tmp.as<Pt>(), bucket_acc.as<Pt>());
     B2S_LAUNCH(c, msm_bucket_segments_kernel<F>, cdiv((uint64_t)segs_per_win * sh.nwin, 128), 128, 0,
                bucket_acc.as<Pt>(), sh, MSM_SEG, segs.as<Pt>());

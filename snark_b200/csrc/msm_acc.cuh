@@ -69,8 +69,9 @@ __device__ __forceinline__ void madd(XYZZ<F>& acc, const Affine<F>& q) {
 template <class F>
 __global__ void __launch_bounds__(MSM_ACC_THREADS)
 msm_accumulate_kernel(const Affine<F>* __restrict__ bases, const uint32_t* __restrict__ sorted,
-                      const uint32_t* __restrict__ offsets, const uint32_t* __restrict__ task_off, MsmShape sh,
-                      XYZZ<F>* __restrict__ bucket_acc, XYZZ<F>* __restrict__ partials) {
+                      const uint32_t* __restrict__ offsets, const uint32_t* __restrict__ task_off,
+                      const uint32_t* __restrict__ perm, MsmShape sh, XYZZ<F>* __restrict__ bucket_acc,
+                      XYZZ<F>* __restrict__ partials) {
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t total = task_off[sh.G];
     if (t >= total) return;
@@ -80,9 +81,11 @@ msm_accumulate_kernel(const Affine<F>* __restrict__ bases, const uint32_t* __res
         const uint32_t mid = (lo + hi) >> 1;
         if (task_off[mid] <= t) lo = mid; else hi = mid;
     }
-    const uint32_t g = lo;
-    const uint32_t k = t - task_off[g];
-    const uint32_t ntasks = task_off[g + 1] - task_off[g];
+    // task_off is indexed by rank; with `perm` the ranks list the buckets by decreasing size so that the
+    // threads of a warp get tasks of (nearly) equal length
+    const uint32_t g = perm ? perm[lo] : lo;
+    const uint32_t k = t - task_off[lo];
+    const uint32_t ntasks = task_off[lo + 1] - task_off[lo];
     const uint32_t beg = offsets[g] + k * sh.L;
     const uint32_t end = min(beg + sh.L, offsets[g + 1]);
 
@@ -113,7 +116,7 @@ __global__ void msm_horner_kernel(const XYZZ<F>* __restrict__ win, MsmShape sh, 
 
 // launches compiled with the multiplication inlined: msm_acc_g1.cu (G1) and msm_acc_g2.cu (G2)
 int32_t msm_accumulate_g2(Ctx* c, const void* bases, const uint32_t* sorted, const uint32_t* offsets,
-                          const uint32_t* task_off, MsmShape sh, void* bucket_acc, void* partials);
+                          const uint32_t* task_off, const uint32_t* perm, MsmShape sh, void* bucket_acc, void* partials);
 int32_t msm_horner_g1(Ctx* c, cudaStream_t st, const void* wins, MsmShape sh, void* out);
 int32_t msm_horner_g2(Ctx* c, cudaStream_t st, const void* wins, MsmShape sh, void* out);
 inline int32_t msm_horner(Ctx* c, cudaStream_t st, int group, const void* wins, MsmShape sh, void* out) {
@@ -121,6 +124,6 @@ inline int32_t msm_horner(Ctx* c, cudaStream_t st, int group, const void* wins, 
 }
 // G1 accumulate for the ctx's curve (msm_acc_g1.cu)
 int32_t msm_accumulate_g1(Ctx* c, const void* bases, const uint32_t* sorted, const uint32_t* offsets,
-                          const uint32_t* task_off, MsmShape sh, void* bucket_acc, void* partials);
+                          const uint32_t* task_off, const uint32_t* perm, MsmShape sh, void* bucket_acc, void* partials);
 
 }  // namespace b2s

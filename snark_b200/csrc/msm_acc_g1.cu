@@ -7,11 +7,11 @@
 namespace b2s {
 
 int32_t msm_accumulate_g1(Ctx* c, const void* bases, const uint32_t* sorted, const uint32_t* offsets,
-                          const uint32_t* task_off, MsmShape sh, void* bucket_acc, void* partials) {
+                          const uint32_t* task_off, const uint32_t* perm, MsmShape sh, void* bucket_acc, void* partials) {
     return dispatch_curve(c, [&](auto curve) {
         using F = typename decltype(curve)::Fq;
         B2S_LAUNCH_N(c, "msm_accumulate_g1", msm_accumulate_kernel<F>, cdiv(sh.max_tasks, MSM_ACC_THREADS), MSM_ACC_THREADS, 0,
-                   reinterpret_cast<const Affine<F>*>(bases), sorted, offsets, task_off, sh,
+                   reinterpret_cast<const Affine<F>*>(bases), sorted, offsets, task_off, perm, sh,
                    reinterpret_cast<XYZZ<F>*>(bucket_acc), reinterpret_cast<XYZZ<F>*>(partials));
         return (int32_t)B2S_OK;
     });
