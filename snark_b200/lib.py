@@ -104,6 +104,13 @@ def _ptr(x):
     if isinstance(x, int):
         return x, MEM_DEVICE
     assert x.is_contiguous()  # torch tensor
+    if x.is_cuda:
+        # The library launches on its own stream (b2s_stream).  Whatever torch queued to produce this tensor must be
+        # finished before that stream reads it; conversely the caller keeps the tensor alive and calls Backend.sync()
+        # before torch touches anything the library wrote (device-memory calls return without synchronising).
+        import torch
+
+        torch.cuda.current_stream(x.device).synchronize()
     return x.data_ptr(), (MEM_DEVICE if x.is_cuda else MEM_HOST)
 
 
