@@ -4,6 +4,10 @@
 #pragma once
 #include "common.cuh"
 
+#ifndef B2S_MADD_BYVALUE
+#define B2S_MADD_BYVALUE 1
+#endif
+
 namespace b2s {
 
 static constexpr int MSM_ACC_THREADS = 128;
@@ -38,9 +42,17 @@ __device__ __forceinline__ void st_struct(T* p, const T& v) {
     for (int i = 0; i < (int)(sizeof(T) / 16); i++) d[i] = s[i];
 }
 
-// rare paths of the mixed addition, kept out of line so the hot loop stays small
+// rare paths of the mixed addition (P + P, P - P), kept out of line so the hot loop stays small.  By value on
+// purpose: passing the accumulator by reference would force it into local memory for the whole loop.
 template <class F>
-__device__ __noinline__ void madd_rare(XYZZ<F>& acc, const Affine<F>& q, bool r_is_zero) {
+__device__ __noinline__ XYZZ<F> madd_rare(Affine<F> q, bool r_is_zero) {
+    if (r_is_zero) return XYZZ<F>::dbl_affine(q);
+    return XYZZ<F>::identity();
+}
+// G2 (Fq2) variant: with 96 accumulator registers the by-value form spills; by reference ptxas keeps the
+// accumulator in (L1-resident) local memory and the kernel stays at 252 registers without spills.
+template <class F>
+__device__ __noinline__ void madd_rare_ref(XYZZ<F>& acc, const Affine<F>& q, bool r_is_zero) {
     if (r_is_zero) acc = XYZZ<F>::dbl_affine(q);
     else acc = XYZZ<F>::identity();
 }
@@ -54,7 +66,12 @@ __device__ __forceinline__ void madd(XYZZ<F>& acc, const Affine<F>& q) {
     }
     F p = q.x * acc.zz - acc.x;
     F r = q.y * acc.zzz - acc.y;
-    if (p.is_zero()) { madd_rare(acc, q, r.is_zero()); return; }
+    if (p.is_zero()) {
+        if (sizeof(F) > 64) madd_rare_ref(acc, q, r.is_zero());
+        else if (B2S_MADD_BYVALUE) acc = madd_rare<F>(q, r.is_zero());
+        else madd_rare_ref(acc, q, r.is_zero());
+        return;
+    }
     F pp = p.sqr();
     F ppp = p * pp;
     F qv = acc.x * pp;
