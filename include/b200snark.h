@@ -147,6 +147,16 @@ typedef struct b2s_pk_desc {
 int32_t b2s_pk_upload(b2s_ctx* ctx, const b2s_pk_desc* desc, int32_t mem, b2s_pk** out);
 void b2s_pk_free(b2s_ctx* ctx, b2s_pk* pk);
 
+/* CircuitSpecificSetupSNARK::setup (snark/src/lib.rs:84-93) on the GPU for uploaded matrices.  `trapdoor` = 5 Montgomery
+ * Fr on the HOST: tau, alpha, beta, gamma, delta, drawn by the caller from its rng (as ark-groth16's generator does).
+ * Returns the device-resident proving key and writes the verifying-key elements to the HOST: alpha_g1 (G1),
+ * beta_g2, gamma_g2, delta_g2 (G2), gamma_abc_g1 (n_instance G1 points). */
+int32_t b2s_groth16_setup(b2s_ctx* ctx, const b2s_r1cs* m, const void* trapdoor, b2s_pk** out_pk, void* out_alpha_g1,
+                          void* out_beta_g2, void* out_gamma_g2, void* out_delta_g2, void* out_gamma_abc_g1);
+/* Copy one vector of a device-resident key to the HOST (to serialise a ProvingKey):
+ * which = 0 a_query, 1 b_g1_query, 2 b_g2_query, 3 h_query, 4 l_query, 5 [alpha,beta,delta]_g1, 6 [beta,delta]_g2. */
+int32_t b2s_pk_query(b2s_ctx* ctx, const b2s_pk* pk, int32_t which, void* out, uint64_t cap_bytes);
+
 /* One proof on one GPU (full key).  z_instance (n_instance, z[0] = 1), z_witness, r, s: Montgomery Fr, HOST.
  * Outputs (HOST): A (G1 affine), B (G2 affine), C (G1 affine) -- `Proof { a, b, c }`. */
 int32_t b2s_groth16_prove(b2s_ctx* ctx, const b2s_pk* pk, const b2s_r1cs* m, const void* z_instance,
@@ -168,6 +178,15 @@ int32_t b2s_groth16_prove_shard_resident(b2s_ctx* ctx, const b2s_pk* pk, const b
 int32_t b2s_groth16_finish(b2s_ctx* ctx, const b2s_pk* pk, const void* g1_partials, const void* g2_partials,
                            uint32_t n_shards, const void* r, const void* s, void* out_a_g1, void* out_b_g2,
                            void* out_c_g1);
+
+/* ---- wire format: CanonicalSerialize::serialize_compressed of group elements / Proof --------
+ * (snark/src/lib.rs:25-36 bounds).  BLS12-381: zcash/IETF big-endian form, 48 B (G1) / 96 B (G2); BN254: ark-ec
+ * SWFlags little-endian form, 32 B / 64 B.  HOST affine Montgomery points in, bytes out; `cap` = size of `out`. */
+int32_t b2s_serialize_g1_compressed(b2s_ctx* ctx, const void* affine, uint32_t count, uint8_t* out, uint64_t cap);
+int32_t b2s_serialize_g2_compressed(b2s_ctx* ctx, const void* affine, uint32_t count, uint8_t* out, uint64_t cap);
+/* Proof { a, b, c } -> a || b || c (192 B on BLS12-381, 128 B on BN254). */
+int32_t b2s_proof_serialize_compressed(b2s_ctx* ctx, const void* a_g1, const void* b_g2, const void* c_g1, uint8_t* out,
+                                       uint64_t cap);
 
 /* ---- setup helper: fixed-base batch multiplication -------------------------
  * out[i] = scalars[i] * G (the curve's standard generator), affine, i < n.  Used to build proving keys

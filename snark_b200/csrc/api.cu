@@ -16,6 +16,7 @@ int32_t field_op_run(Ctx* c, int field, int op, const void* a, const void* b, vo
 int32_t group_op_run(Ctx* c, int group, int op, const void* a, const void* b, const void* k, void* out, uint64_t count);
 int32_t fixed_base_run(Ctx* c, int group, const void* scalars_dev, uint64_t n, bool mont, void* out_dev);
 void fixed_base_free(Ctx* c);
+int32_t serialize_points(Ctx* c, int group, const void* affine_host, uint32_t count, uint8_t* out, uint64_t cap);
 }  // namespace b2s
 
 #define LOCK(ctx)                                      \
@@ -418,6 +419,45 @@ int32_t b2s_profile_report(b2s_ctx* ctx, char* buf, uint64_t cap) {
     memcpy(buf, out.data(), nn);
     buf[nn] = 0;
     return B2S_OK;
+}
+
+
+int32_t b2s_groth16_setup(b2s_ctx* ctx, const b2s_r1cs* m, const void* trapdoor, b2s_pk** out_pk, void* out_alpha_g1,
+                          void* out_beta_g2, void* out_gamma_g2, void* out_delta_g2, void* out_gamma_abc_g1) {
+    LOCK(ctx);
+    if (!m) return fail(ctx, B2S_ERR_MISSING_CS, "setup: null matrices");
+    if (!trapdoor || !out_pk || !out_alpha_g1 || !out_beta_g2 || !out_gamma_g2 || !out_delta_g2 || !out_gamma_abc_g1)
+        return fail(ctx, B2S_ERR_INVALID_ARG, "setup: null argument");
+    *out_pk = nullptr;
+    return groth16_setup(ctx, m, trapdoor, out_pk, out_alpha_g1, out_beta_g2, out_gamma_g2, out_delta_g2, out_gamma_abc_g1);
+}
+
+int32_t b2s_pk_query(b2s_ctx* ctx, const b2s_pk* pk, int32_t which, void* out, uint64_t cap_bytes) {
+    LOCK(ctx);
+    if (!pk || !out) return fail(ctx, B2S_ERR_INVALID_ARG, "pk_query: null argument");
+    return pk_query_download(ctx, pk, which, out, cap_bytes);
+}
+
+
+int32_t b2s_serialize_g1_compressed(b2s_ctx* ctx, const void* affine, uint32_t count, uint8_t* out, uint64_t cap) {
+    LOCK(ctx);
+    if ((!affine || !out) && count) return fail(ctx, B2S_ERR_INVALID_ARG, "serialize: null buffer");
+    return serialize_points(ctx, 1, affine, count, out, cap);
+}
+int32_t b2s_serialize_g2_compressed(b2s_ctx* ctx, const void* affine, uint32_t count, uint8_t* out, uint64_t cap) {
+    LOCK(ctx);
+    if ((!affine || !out) && count) return fail(ctx, B2S_ERR_INVALID_ARG, "serialize: null buffer");
+    return serialize_points(ctx, 2, affine, count, out, cap);
+}
+int32_t b2s_proof_serialize_compressed(b2s_ctx* ctx, const void* a_g1, const void* b_g2, const void* c_g1, uint8_t* out,
+                                       uint64_t cap) {
+    LOCK(ctx);
+    if (!a_g1 || !b_g2 || !c_g1 || !out) return fail(ctx, B2S_ERR_INVALID_ARG, "proof_serialize: null buffer");
+    const uint64_t fq = ctx->curve == B2S_CURVE_BLS12_381 ? 48 : 32;
+    if (cap < 4 * fq) return fail(ctx, B2S_ERR_INVALID_ARG, "proof_serialize: output buffer too small");
+    B2S_TRY(serialize_points(ctx, 1, a_g1, 1, out, fq));
+    B2S_TRY(serialize_points(ctx, 2, b_g2, 1, out + fq, 2 * fq));
+    return serialize_points(ctx, 1, c_g1, 1, out + 3 * fq, fq);
 }
 
 }  // extern "C"

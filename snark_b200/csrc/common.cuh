@@ -151,6 +151,8 @@ void ntt_free_plans(Ctx* c);
 int32_t msm_run(Ctx* c, int group, const void* bases_dev, const void* scalars_dev, uint64_t n, bool scalars_mont,
                 void* out_xyzz_dev, void* wins_ext = nullptr);
 int32_t msm_join_tails(Ctx* c);
+int32_t scan_counts(Ctx* c, const uint32_t* counts, uint32_t n, uint32_t L, uint32_t* offsets, uint32_t* task_off);
+int32_t fixed_base_run(Ctx* c, int group, const void* scalars_dev, uint64_t n, bool mont, void* out_dev);
 int32_t group_sum_to_affine(Ctx* c, int group, const void* xyzz_dev, uint32_t count, void* out_affine_dev);
 
 }  // namespace b2s

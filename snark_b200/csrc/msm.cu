@@ -551,6 +551,23 @@ static int32_t msm_run_t(Ctx* c, const void* bases_dev, const void* scalars_dev,
     return B2S_OK;
 }
 
+// Generic use of the scan kernels (setup_groth16.cu: column-sorted matrices): offsets[i] = sum_{j<i} counts[j],
+// task_off[i] = sum_{j<i} ceil(counts[j] / L); both arrays have n + 1 entries.
+int32_t scan_counts(Ctx* c, const uint32_t* counts, uint32_t n, uint32_t L, uint32_t* offsets, uint32_t* task_off) {
+    MsmShape sh{};
+    sh.G = n;
+    sh.L = L;
+    const uint32_t ntiles = (n + SCAN_TILE - 1) / SCAN_TILE;
+    DevBuf tiles, heavy;
+    B2S_TRY(tiles.alloc(c, (size_t)ntiles * sizeof(Scan3)));
+    B2S_TRY(heavy.alloc(c, ((size_t)n + 1) * sizeof(uint32_t)));
+    const uint32_t* no_perm = nullptr;
+    B2S_LAUNCH(c, msm_scan_tiles_kernel, ntiles, SCAN_THREADS, 0, counts, no_perm, sh, tiles.as<Scan3>());
+    B2S_LAUNCH(c, msm_scan_spine_kernel, 1, 1024, 0, tiles.as<Scan3>(), ntiles, sh, offsets, task_off, heavy.as<uint32_t>());
+    B2S_LAUNCH(c, msm_scan_apply_kernel, ntiles, SCAN_THREADS, 0, counts, no_perm, sh, tiles.as<Scan3>(), offsets, task_off, heavy.as<uint32_t>());
+    return B2S_OK;
+}
+
 int32_t msm_join_tails(Ctx* c) {
     if (!c->aux_pending) return B2S_OK;
     B2S_CUDA(c, cudaEventRecord(c->ev_done, c->aux));

@@ -32,6 +32,9 @@ int32_t spmv_run(Ctx* c, const b2s_r1cs* m, const void* z_dev, void* out_a, void
 // h_dev: device array of domain elements (output); z_dev: n_instance + n_witness elements
 int32_t witness_map_run(Ctx* c, const b2s_r1cs* m, const void* z_dev, void* h_dev);
 int32_t pk_upload(Ctx* c, const b2s_pk_desc* d, int32_t mem, b2s_pk** out);
+int32_t groth16_setup(Ctx* c, const b2s_r1cs* m, const void* trapdoor_host, b2s_pk** out_pk, void* o_alpha_g1, void* o_beta_g2,
+                      void* o_gamma_g2, void* o_delta_g2, void* o_gamma_abc);
+int32_t pk_query_download(Ctx* c, const b2s_pk* pk, int which, void* out_host, uint64_t cap_bytes);
 // z either as two host pieces (z_dev == nullptr) or as one device array
 int32_t groth16_shard(Ctx* c, const b2s_pk* pk, const b2s_r1cs* m, const void* z_inst_host, const void* z_wit_host,
                       const void* z_dev, const void* r_host, const void* s_host, void* g1_partials_dev /*4 xyzz*/,

@@ -60,6 +60,8 @@ SIGNATURES = {
     "b2s_r1cs_domain_size": (c_uint64, [c_void_p]),
     "b2s_pk_upload": (c_int32, [c_void_p, POINTER(PkDesc), c_int32, POINTER(c_void_p)]),
     "b2s_pk_free": (None, [c_void_p, c_void_p]),
+    "b2s_groth16_setup": (c_int32, [c_void_p, c_void_p, c_void_p, POINTER(c_void_p)] + [c_void_p] * 5),
+    "b2s_pk_query": (c_int32, [c_void_p, c_void_p, c_int32, c_void_p, c_uint64]),
     "b2s_groth16_prove": (c_int32, [c_void_p] * 10),
     "b2s_groth16_prove_shard": (c_int32, [c_void_p] * 9),
     "b2s_groth16_prove_resident": (c_int32, [c_void_p] * 9),
@@ -68,6 +70,9 @@ SIGNATURES = {
     "b2s_profile_report": (c_int32, [c_void_p, c_char_p, c_uint64]),
     "b2s_groth16_finish": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_uint32, c_void_p, c_void_p, c_void_p,
                                      c_void_p, c_void_p]),
+    "b2s_serialize_g1_compressed": (c_int32, [c_void_p, c_void_p, c_uint32, c_void_p, c_uint64]),
+    "b2s_serialize_g2_compressed": (c_int32, [c_void_p, c_void_p, c_uint32, c_void_p, c_uint64]),
+    "b2s_proof_serialize_compressed": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_uint64]),
     "b2s_fixed_base_g1": (c_int32, [c_void_p, c_void_p, c_uint64, c_int32, c_int32, c_void_p]),
     "b2s_fixed_base_g2": (c_int32, [c_void_p, c_void_p, c_uint64, c_int32, c_int32, c_void_p]),
     "b2s_field_op": (c_int32, [c_void_p, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_uint64]),
@@ -253,6 +258,35 @@ class Backend:
         h = c_void_p()
         self._ck(self.lib.b2s_pk_upload(self.h, ctypes.byref(desc), mem, ctypes.byref(h)))
         return h
+
+    def groth16_setup(self, m, trapdoor, n_instance):
+        """trapdoor: uint32[5*8] Montgomery (tau, alpha, beta, gamma, delta) -> (pk handle, vk dict of numpy arrays)."""
+        h = c_void_p()
+        vk = {"alpha_g1": np.zeros(self.g1_bytes // 4, dtype=np.uint32), "beta_g2": np.zeros(self.g2_bytes // 4, dtype=np.uint32),
+              "gamma_g2": np.zeros(self.g2_bytes // 4, dtype=np.uint32), "delta_g2": np.zeros(self.g2_bytes // 4, dtype=np.uint32),
+              "gamma_abc_g1": np.zeros(max(n_instance, 1) * self.g1_bytes // 4, dtype=np.uint32)}
+        self._ck(self.lib.b2s_groth16_setup(self.h, m, trapdoor.ctypes.data, ctypes.byref(h), vk["alpha_g1"].ctypes.data,
+                                            vk["beta_g2"].ctypes.data, vk["gamma_g2"].ctypes.data, vk["delta_g2"].ctypes.data,
+                                            vk["gamma_abc_g1"].ctypes.data))
+        return h, vk
+
+    def pk_query(self, pk, which, count):
+        per = self.g2_bytes if which in (2, 6) else self.g1_bytes
+        out = np.zeros(count * per // 4, dtype=np.uint32)
+        self._ck(self.lib.b2s_pk_query(self.h, pk, which, out.ctypes.data, out.nbytes))
+        return out
+
+    def serialize_points(self, group, affine, count):
+        per = (self.fq_bytes if group == 1 else 2 * self.fq_bytes)
+        out = np.zeros(count * per, dtype=np.uint8)
+        fn = self.lib.b2s_serialize_g1_compressed if group == 1 else self.lib.b2s_serialize_g2_compressed
+        self._ck(fn(self.h, affine.ctypes.data, count, out.ctypes.data, out.nbytes))
+        return out.tobytes()
+
+    def proof_bytes(self, a, b, c):
+        out = np.zeros(4 * self.fq_bytes, dtype=np.uint8)
+        self._ck(self.lib.b2s_proof_serialize_compressed(self.h, a.ctypes.data, b.ctypes.data, c.ctypes.data, out.ctypes.data, out.nbytes))
+        return out.tobytes()
 
     def pk_free(self, pk):
         self.lib.b2s_pk_free(self.h, pk)

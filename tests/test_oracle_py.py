@@ -143,3 +143,21 @@ def test_groth16_known_trapdoor(curve):
         _, _, _, hb = og.prove(pk, mats, inst, bad, rr, ss)
         eb = og.expected_proof_exponents(pk, inst, bad, hb, rr, ss)
         assert not og.verify_equation_in_exponent(pk, inst, *eb)
+
+
+def test_compressed_encoding_known_vectors():
+    """the standard compressed BLS12-381 generators pin the zcash-form encoder."""
+    from oracle import serialize as oser
+
+    G1, G2 = groups(BLS12_381)
+    assert oser.point_compressed(BLS12_381, 1, G1.gen).hex() == (
+        "97f1d3a73197d7942695638c4fa9ac0fc3688c4f9774b905a14e3a3f171bac586c55e83ff97a1aeffb3af00adb22c6bb")
+    assert oser.point_compressed(BLS12_381, 2, G2.gen).hex() == (
+        "93e02b6052719f607dacd3a088274f65596bd0d09920b61ab5da61bbdc7f5049334cf11213945d57e5ac7d055d042b7e"
+        "024aa2b2f08f0a91260805272dc51051c6e47ad4fa403b02b4510b647ae3d1770bac0326a805bbefd48056c8c121bdb8")
+    assert oser.point_compressed(BLS12_381, 1, None) == bytes([0xC0]) + bytes(47)
+    assert oser.point_compressed(BLS12_381, 1, G1.neg(G1.gen))[0] == 0xB7
+    g = groups(BN254)[0]
+    assert oser.point_compressed(BN254, 1, g.gen) == (1).to_bytes(32, "little")
+    assert oser.point_compressed(BN254, 1, g.neg(g.gen))[-1] & 0x80
+    assert len(oser.proof_compressed(BN254, g.gen, groups(BN254)[1].gen, None)) == 128
