@@ -342,7 +342,12 @@ def run_b200(args):
     share = tot_ms / sum(v[1] for v in rep.values())
     pts_per_launch = {"msm_accumulate_g1": (N - 1) / world, "msm_accumulate_g2": (N - 1) / world}.get(kern)
     bytes_per_pt = {"msm_accumulate_g1": 128, "msm_accumulate_g2": 224}.get(kern)
-    roof = {"kernel": kern, "bound": "hbm", "unit": "GB/s", "peak": peak, "peak_source": peak_src, "traffic": None,
+    # dram__bytes_read.sum + dram__bytes_write.sum per launch from `ncu --set full` captures of this kernel at this
+    # size (profiles/r01b_msm_accumulate_g1_ncu.txt, r01b_msm_accumulate_ncu.txt); null for sizes not captured.
+    # ~20x the algorithmic bytes BY CONSTRUCTION: the bucket method gathers every base once per window (13 x 96 B,
+    # fetched as 128-B lines), it is not re-read waste; DRAM is 7 % busy, the fmaheavy pipe 85 %.
+    traffic = {("msm_accumulate_g1", 24, 1): 43.77e9, ("msm_accumulate_g2", 24, 1): 44.25e9}.get((kern, args.log_n, world))
+    roof = {"kernel": kern, "bound": "hbm", "unit": "GB/s", "peak": peak, "peak_source": peak_src, "traffic": traffic,
             "launches": cnt, "avg_launch_ms": tot_ms / cnt, "share_of_step": share}
     if pts_per_launch:
         alg = pts_per_launch * bytes_per_pt
