@@ -4,6 +4,9 @@
 #pragma once
 #include "common.cuh"
 
+#ifndef B2S_G2_MIN_BLOCKS
+#define B2S_G2_MIN_BLOCKS 1   // CTAs/SM the G2 accumulate kernel is compiled for (register cap = 65536 / (128 * this))
+#endif
 #ifndef B2S_MADD_BYVALUE
 #define B2S_MADD_BYVALUE 1
 #endif
@@ -84,7 +87,7 @@ __device__ __forceinline__ void madd(XYZZ<F>& acc, const Affine<F>& q) {
 
 // One thread per task.  Task t belongs to bucket g = upper_bound(task_off, t) - 1.
 template <class F>
-__global__ void __launch_bounds__(MSM_ACC_THREADS)
+__global__ void __launch_bounds__(MSM_ACC_THREADS, (sizeof(F) > 64 ? B2S_G2_MIN_BLOCKS : 1))
 msm_accumulate_kernel(const Affine<F>* __restrict__ bases, const uint32_t* __restrict__ sorted,
                       const uint32_t* __restrict__ offsets, const uint32_t* __restrict__ task_off,
                       const uint32_t* __restrict__ perm, MsmShape sh, XYZZ<F>* __restrict__ bucket_acc,
