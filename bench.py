@@ -95,10 +95,6 @@ def rs_scalars():
     return mont(r), mont(s)
 
 
-def shard_range(total, rank, world):
-    return total * rank // world, total * (rank + 1) // world
-
-
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
 
@@ -243,7 +239,7 @@ def run_b200(args):
         return t
 
     def make_query(group, total, seed):
-        lo, hi = shard_range(total, rank, world)
+        lo, hi = shard.shard_range(total, rank, world)
         k = rand_scalars(hi - lo, seed * 1000 + rank)
         out = torch.empty(((hi - lo) * (be.g1_bytes if group == 1 else be.g2_bytes)) // 4, dtype=torch.int32, device=dev)
         be.fixed_base(group, k, hi - lo, mont=False, out=out)
@@ -273,7 +269,6 @@ def run_b200(args):
     r, s = rs_scalars()
     z_host = torch.from_numpy(np.concatenate([inst["z_inst"], inst["z_wit"]]).view(np.int32)).pin_memory()
     z_dev = z_host.to(dev)
-    gather_words = (4 * be.g1x_bytes + be.g2x_bytes) // 4
 
     def prove(resident):
         """One proof; returns the proof (rank 0) -- every rank takes part."""

@@ -5,18 +5,22 @@
 // Appendix A.1).  The output is a group element, so after normalisation it is bit-identical to any
 // other correct MSM regardless of window size or summation order.
 //
-// Pipeline (all on the ctx stream, no host synchronisation inside):
+// Pipeline (no host synchronisation inside; everything on the ctx stream except the Horner tail, which can run on
+// the ctx's aux stream so that it overlaps the next MSM of a proof):
 //   1 count     one thread per scalar: Montgomery -> canonical, signed digits, histogram of
-//               (window, |digit|) bucket sizes (global atomics, 4 B each)
+//               (window, |digit|) bucket sizes (warp-aggregated global atomics, 4 B each)
 //   2 scan      exclusive prefix sums (tile sums, spine, apply): bucket offsets in the sorted index array, and task offsets
 //               (a bucket of s points is cut into ceil(s / L) tasks so that no thread ever owns more
 //               than L points -- this is what keeps degenerate scalar distributions, e.g. the all-equal
 //               witness of the reference's DummyCircuit (relations/src/sr1cs/mod.rs:306-309), balanced)
 //   3 scatter   counting-sort the point indices (sign in bit 31) by bucket
+//   3a rank     buckets are ranked by decreasing size (second counting sort) and task numbers follow the ranks, so
+//               the 32 tasks a warp runs in lockstep have equal length (uniform scalars give Poisson bucket sizes)
+//   3b (off by default, B2S_MSM_AFFINE_ROUNDS) batched-affine halving rounds, msm_affine.cuh
 //   4 accumulate one thread per task: XYZZ accumulator += affine base, 8M+2S per point; bases are
 //               gathered from HBM (96 B / 192 B per point), everything else stays in registers
-//   5 reduce    buckets that were split: one CTA sums the task partials of a bucket (shared-memory tree)
-//   6 bucket sum per window sum_b b*B_b by segments: running sums over 16 buckets per thread, then
+//   5 reduce    buckets that were split: CTAs sum the task partials of a bucket (two stages, shared-memory tree)
+//   6 bucket sum per window sum_b b*B_b by segments: running sums over 16-32 buckets per thread, then
 //               seg_start * (segment total) by double-and-add; one CTA per window adds the segments
 //   7 horner    sum_w 2^(c w) S_w, one thread (255 doublings; multiplication inlined for ILP, msm_acc_g*.cu)
 //

@@ -138,7 +138,7 @@ __global__ void __launch_bounds__(NTT_THREADS) ntt_pass_strided(const Fr* __rest
     const uint32_t R = 1u << a.log_r, C = 1u << a.log_c;
     const uint32_t pitch = 2 * C + 1;
     uint4* tile = smem;
-    Fr* wtab = reinterpret_cast<Fr*>(smem + (size_t)R * pitch + 1);  // keep 32 B alignment irrelevant: Fr is 4-byte aligned
+    Fr* wtab = reinterpret_cast<Fr*>(smem + (size_t)R * pitch + 1);   // twiddles w_R^e behind the tile (16-byte aligned)
     const uint32_t tiles_per_p = 1u << (a.log_m - a.log_c);
     const uint64_t p = blockIdx.x / tiles_per_p;
     const uint64_t m0 = (uint64_t)(blockIdx.x % tiles_per_p) << a.log_c;
