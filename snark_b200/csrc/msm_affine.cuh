@@ -75,16 +75,41 @@ msm_ba_round_kernel(const Affine<F>* __restrict__ bases, const uint32_t* __restr
     }
     const uint32_t g0 = lo;
 
-    // ---- pass 1: prefix products of the denominators
+    // ---- pass 1: prefix products of the denominators.  Only the x coordinates are needed unless a pair is special
+    // (missing partner, x = 0 which may be the (0,0) encoding of infinity, or equal x): then the y's are fetched and
+    // the pair is classified exactly as pass 2 will.  The next pair's x's are requested before the current
+    // multiplication so that the gather latency hides behind it.
     F prod = F::one();
     {
         uint32_t g = g0, g_out_end = out_off[g + 1], g_in = in_off[g], g_in_end = in_off[g + 1], g_out = out_off[g];
-        for (uint32_t o = o_beg; o < o_end; o++) {
+        struct Xs { F x1, x2; uint32_t in0; bool has2; };
+        auto fetch = [&](uint32_t o) {
             while (o >= g_out_end) { g++; g_out = out_off[g]; g_out_end = out_off[g + 1]; g_in = in_off[g]; g_in_end = in_off[g + 1]; }
-            const uint32_t in0 = g_in + 2 * (o - g_out);
-            BaPair<F> q = ba_load<F, FIRST>(bases, sorted, prev, in0, in0 + 1 < g_in_end);
+            Xs r;
+            r.in0 = g_in + 2 * (o - g_out);
+            r.has2 = r.in0 + 1 < g_in_end;
+            if (FIRST) {
+                r.x1 = ld_struct(&bases[sorted[r.in0] & 0x7fffffffu].x);
+                r.x2 = r.has2 ? ld_struct(&bases[sorted[r.in0 + 1] & 0x7fffffffu].x) : F::zero();
+            } else {
+                r.x1 = ld_struct(&prev[r.in0].x);
+                r.x2 = r.has2 ? ld_struct(&prev[r.in0 + 1].x) : F::zero();
+            }
+            return r;
+        };
+        Xs nxt = fetch(o_beg);
+        for (uint32_t o = o_beg; o < o_end; o++) {
+            const Xs cur = nxt;
+            if (o + 1 < o_end) nxt = fetch(o + 1);
+            F d;
+            if (cur.has2 && !cur.x1.is_zero() && !cur.x2.is_zero() && cur.x1 != cur.x2) {
+                d = cur.x2 - cur.x1;
+            } else {
+                BaPair<F> q = ba_load<F, FIRST>(bases, sorted, prev, cur.in0, cur.has2);   // rare: full classification
+                d = ba_denominator(q);
+            }
             st_struct(prefix + o, prod);
-            prod = prod * ba_denominator(q);
+            prod = prod * d;
         }
     }
     F inv = prod.inverse();
