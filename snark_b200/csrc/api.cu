@@ -399,9 +399,11 @@ int32_t b2s_profile_report(b2s_ctx* ctx, char* buf, uint64_t cap) {
     if (!buf || cap == 0) return fail(ctx, B2S_ERR_INVALID_ARG, "profile_report: null buffer");
     B2S_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     std::map<std::string, std::pair<uint64_t, double>> agg;
+    const bool verbose = getenv("B2S_PROFILE_VERBOSE") != nullptr;
     for (auto& r : ctx->prof) {
         float ms = 0.f;
         cudaEventElapsedTime(&ms, r.e0, r.e1);
+        if (verbose) fprintf(stderr, "[b2s-profile] %-40s %.3f ms\n", r.name, ms);
         auto& a = agg[r.name];
         a.first++;
         a.second += ms;

@@ -16,7 +16,8 @@
 //   3 scatter   counting-sort the point indices (sign in bit 31) by bucket
 //   3a rank     buckets are ranked by decreasing size (second counting sort) and task numbers follow the ranks, so
 //               the 32 tasks a warp runs in lockstep have equal length (uniform scalars give Poisson bucket sizes)
-//   3b (off by default, B2S_MSM_AFFINE_ROUNDS=r) batched-affine halving rounds, msm_affine.cuh, instead of 3a
+//   3b for big problems (windows * n >= 2^27; B2S_MSM_AFFINE_ROUNDS overrides) three batched-affine halving rounds,
+//               msm_affine.cuh, instead of 3a
 //   4 accumulate one thread per task: XYZZ accumulator += affine base, 8M+2S per point; bases are
 //               gathered from HBM (96 B / 192 B per point), everything else stays in registers
 //   5 reduce    buckets that were split: CTAs sum the task partials of a bucket (two stages, shared-memory tree)
@@ -462,6 +463,7 @@ static int32_t msm_run_t(Ctx* c, const void* bases_dev, const void* scalars_dev,
     const uint32_t segs_per_win = (sh.B + MSM_SEG - 1) / MSM_SEG;
     B2S_TRY(segs.alloc(c, (size_t)segs_per_win * sh.nwin * sizeof(Pt)));
     if (sh.nwin > 64) wins_ext = nullptr;   // caller scratch holds 64 window sums; tiny windows take the in-stream path
+    if (getenv("B2S_NO_AUX")) wins_ext = nullptr;   // debugging knob: keep the Horner tail on the main stream
     if (!wins_ext) B2S_TRY(wins.alloc(c, (size_t)sh.nwin * sizeof(Pt)));
     Pt* wins_p = wins_ext ? reinterpret_cast<Pt*>(wins_ext) : wins.as<Pt>();
 
@@ -473,11 +475,10 @@ static int32_t msm_run_t(Ctx* c, const void* bases_dev, const void* scalars_dev,
     B2S_LAUNCH(c, msm_scatter_kernel<Fr>, cdiv(n, 256), 256, 0, scalars, n, mont, sh, offsets, cursor, sorted.as<uint32_t>());
     constexpr bool is_g1 = sizeof(F) == sizeof(typename Curve::Fq);
     // optional batched-affine halving rounds (msm_affine.cuh); afterwards the points are already in bucket order
-    // OFF by default.  Stand-alone MSMs at 2^24 points gain 10-13 % on skewed scalars with three rounds at K = 512
-    // (G1 89 -> 79 ms, G2 276 -> 239 ms; neutral on uniform scalars), but inside b2s_groth16_prove the same round
-    // kernels ran ~6x slower (2466 vs 680 ms per proof, profiles/r01_experiments.md) for a reason not yet understood
-    // (suspect: placement of the 30 GB of per-round scratch in the stream-ordered pool next to the resident key).
-    const uint32_t ba_rounds = env_u32("B2S_MSM_AFFINE_ROUNDS", 0);
+    // On for big problems only: at 2^24 points three rounds with K = 512 take 10-13 % off skewed-scalar MSMs (G1 89 -> 79
+    // ms, G2 276 -> 239 ms) and are neutral on uniform ones; below ~2^23 points the rounds do not fill the GPU at
+    // that K.  (profiles/r01_experiments.md)
+    const uint32_t ba_rounds = env_u32("B2S_MSM_AFFINE_ROUNDS", (uint64_t)sh.nwin * n >= (1ull << 27) ? 3u : 0u);
     const uint32_t ba_k = max(1u, env_u32("B2S_MSM_AFFINE_K", 512));
     const void* acc_bases = bases;
     const uint32_t* acc_sorted = sorted.as<uint32_t>();

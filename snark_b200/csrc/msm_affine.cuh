@@ -56,6 +56,30 @@ __device__ __forceinline__ F ba_denominator(const BaPair<F>& q) {
     return F::one();
 }
 
+// Bucket of output `o`: the largest g with off[g] <= o (empty buckets have off[g] == off[g+1] and are skipped).
+// `hint` is a bucket at or before it.  The next bucket is tried first (dense case); otherwise a binary search --
+// never a linear walk: with skewed scalars two non-empty buckets can be 2^19 empty ones apart.
+__device__ __forceinline__ uint32_t ba_bucket_fwd(const uint32_t* __restrict__ off, uint32_t G, uint32_t hint, uint32_t o) {
+    if (off[hint + 1] > o) return hint;
+    if (hint + 2 <= G && off[hint + 2] > o) return hint + 1;
+    uint32_t lo = hint + 1, hi = G;          // off[lo] <= o < off[hi]
+    while (hi - lo > 1) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (off[mid] <= o) lo = mid; else hi = mid;
+    }
+    return lo;
+}
+// same, searching downwards from a bucket `hint` whose range starts after o
+__device__ __forceinline__ uint32_t ba_bucket_bwd(const uint32_t* __restrict__ off, uint32_t hint, uint32_t o) {
+    if (hint > 0 && off[hint - 1] <= o) return hint - 1;
+    uint32_t lo = 0, hi = hint;              // off[lo] <= o < off[hi]
+    while (hi - lo > 1) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (off[mid] <= o) lo = mid; else hi = mid;
+    }
+    return lo;
+}
+
 // One thread: outputs [t*K, (t+1)*K) of this round.
 template <class F, bool FIRST>
 __global__ void __launch_bounds__(BA_THREADS)
@@ -84,7 +108,7 @@ msm_ba_round_kernel(const Affine<F>* __restrict__ bases, const uint32_t* __restr
         uint32_t g = g0, g_out_end = out_off[g + 1], g_in = in_off[g], g_in_end = in_off[g + 1], g_out = out_off[g];
         struct Xs { F x1, x2; uint32_t in0; bool has2; };
         auto fetch = [&](uint32_t o) {
-            while (o >= g_out_end) { g++; g_out = out_off[g]; g_out_end = out_off[g + 1]; g_in = in_off[g]; g_in_end = in_off[g + 1]; }
+            if (o >= g_out_end) { g = ba_bucket_fwd(out_off, G, g, o); g_out = out_off[g]; g_out_end = out_off[g + 1]; g_in = in_off[g]; g_in_end = in_off[g + 1]; }
             Xs r;
             r.in0 = g_in + 2 * (o - g_out);
             r.has2 = r.in0 + 1 < g_in_end;
@@ -116,11 +140,10 @@ msm_ba_round_kernel(const Affine<F>* __restrict__ bases, const uint32_t* __restr
     // ---- pass 2: backwards
     {
         // bucket of the last output
-        uint32_t g = g0;
-        while (out_off[g + 1] <= o_end - 1) g++;
+        uint32_t g = ba_bucket_fwd(out_off, G, g0, o_end - 1);
         uint32_t g_out = out_off[g], g_in = in_off[g], g_in_end = in_off[g + 1];
         for (uint32_t o = o_end; o-- > o_beg;) {
-            while (o < g_out) { g--; g_out = out_off[g]; g_in = in_off[g]; g_in_end = in_off[g + 1]; }
+            if (o < g_out) { g = ba_bucket_bwd(out_off, g, o); g_out = out_off[g]; g_in = in_off[g]; g_in_end = in_off[g + 1]; }
             const uint32_t in0 = g_in + 2 * (o - g_out);
             BaPair<F> q = ba_load<F, FIRST>(bases, sorted, prev, in0, in0 + 1 < g_in_end);
             const F d = ba_denominator(q);

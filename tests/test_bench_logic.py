@@ -1,0 +1,38 @@
+"""bench.py's pure logic on the CPU: synthetic-instance shape, add counts, and the roofline object built from a
+per-kernel timing report (a report captured on the B200 is replayed here)."""
+import json
+import os
+
+import bench
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_dummy_instance_shape():
+    inst = bench.dummy_instance(6)
+    assert inst["N"] == 64 and inst["n_rows"] + inst["n_inst"] == 64 and inst["n_inst"] + inst["n_wit"] == 63
+    rp, col, co = inst["csr"][0]
+    assert rp[0] == 0 and rp[-1] == inst["n_rows"] - 1 and rp[-2] == rp[-1]          # last constraint is empty
+    assert set(col.tolist()) == {2} and len(co) == 8 * (inst["n_rows"] - 1)
+    assert bench.reference_add_count(1 << 22) == 64880640
+    assert bench.msm_window_choice(1 << 24, 192) == (20, 13)
+
+
+def test_roofline_from_report():
+    d = json.load(open(os.path.join(ROOT, "profiles", "r01_final_bench_n1.json")))
+    rep = {k: (1, v * d["steps"]) for k, v in d["kernel_ms_per_step"].items()}
+    rep["msm_accumulate_g1"] = (4 * d["steps"], rep["msm_accumulate_g1"][1])
+    rep["msm_accumulate_g2"] = (d["steps"], rep["msm_accumulate_g2"][1])
+    roof = bench.roofline_from_report(rep, 1 << 24, 1, 24, 6569.6, "measured")
+    assert roof["kernel"].startswith("msm bucket accumulation g1") and roof["traffic"] == 43.77e9
+    assert abs(roof["frac"] - d["roofline"]["frac"]) < 1e-4 and 0.85 < roof["alu"]["frac"] < 1.0
+    # with the batched-affine rounds the three round launches and the XYZZ pass count as one unit per MSM
+    rep2 = dict(rep)
+    rep2["msm_ba_round_g1"] = (12 * d["steps"], 249.6 * d["steps"])
+    rep2["msm_accumulate_g1"] = (4 * d["steps"], 48.3 * d["steps"])
+    roof2 = bench.roofline_from_report(rep2, 1 << 24, 1, 24, 6569.6, "measured")
+    assert roof2["traffic"] is None and roof2["launch_unit"].startswith("one MSM")
+    assert abs(roof2["avg_launch_ms"] - (249.6 + 48.3) / 4) < 1e-6 and roof2["achieved"] > roof["achieved"]
+    # a report without MSM kernels still yields a well-formed object
+    roof3 = bench.roofline_from_report({"ntt_pass_final<Fr>": (3, 4.5)}, 1 << 24, 1, 24, 6569.6, "measured")
+    assert roof3["kernel"] == "ntt_pass_final<Fr>" and roof3["avg_launch_ms"] == 1.5
