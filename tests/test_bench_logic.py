@@ -19,7 +19,7 @@ def test_dummy_instance_shape():
 
 
 def test_roofline_from_report():
-    d = json.load(open(os.path.join(ROOT, "profiles", "r01_final_bench_n1.json")))
+    d = json.load(open(os.path.join(ROOT, "profiles", "r01_bench_n1_xyzz_only.json")))
     rep = {k: (1, v * d["steps"]) for k, v in d["kernel_ms_per_step"].items()}
     rep["msm_accumulate_g1"] = (4 * d["steps"], rep["msm_accumulate_g1"][1])
     rep["msm_accumulate_g2"] = (d["steps"], rep["msm_accumulate_g2"][1])
