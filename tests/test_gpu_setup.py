@@ -10,7 +10,7 @@ from oracle import groth16 as og
 from oracle import r1cs as orc
 from oracle.ec import groups
 from oracle.params import BLS12_381, BN254
-from tests.util import csr_from_rows, pack_fr, unpack_points
+from tests.util import csr_from_rows, pack_fr, pairing_verify_packed, unpack_points
 
 pytestmark = pytest.mark.gpu
 CURVES = [BLS12_381, BN254]
@@ -55,6 +55,9 @@ def test_setup_matches_oracle_and_proves(be):
         A, B, C, _ = og.prove(pk, mats, inst, wit, rr, ss)
         a, b, c = be.groth16_prove(pkh, m, pack_fr(curve, inst), pack_fr(curve, wit), pack_fr(curve, [rr]), pack_fr(curve, [ss]))
         assert (unpack_points(curve, 1, a)[0], unpack_points(curve, 2, b)[0], unpack_points(curve, 1, c)[0]) == (A, B, C), name
+        if curve is BLS12_381:
+            # SNARK::verify with real pairings on the GPU's own key and proof (no trapdoor involved)
+            assert pairing_verify_packed(curve, vk, len(inst), inst, (a, b, c)), name
         be.pk_free(pkh); be.r1cs_free(m)
 
 

@@ -126,3 +126,21 @@ def limbs_to_ints(arr, n=8):
     for j in range(1, n):
         acc = acc + (a[:, j] << (32 * j))
     return list(acc)
+
+
+def pairing_verify_packed(curve, vk, n_instance, z_inst, proof_abc):
+    """Groth16 verification with real pairings (oracle/pairing.py) on C-ABI arrays: `vk` as returned by
+    Backend.groth16_setup (dict of uint32 arrays), z_inst the instance assignment INCLUDING the leading 1 (ints),
+    proof_abc the three uint32 arrays of Backend.groth16_prove.  BLS12-381 only."""
+    from oracle import pairing
+
+    vk_pts = {
+        "alpha_g1": unpack_points(curve, 1, vk["alpha_g1"])[0],
+        "beta_g2": unpack_points(curve, 2, vk["beta_g2"])[0],
+        "gamma_g2": unpack_points(curve, 2, vk["gamma_g2"])[0],
+        "delta_g2": unpack_points(curve, 2, vk["delta_g2"])[0],
+        "gamma_abc_g1": unpack_points(curve, 1, vk["gamma_abc_g1"])[:n_instance],
+    }
+    a, b, c = proof_abc
+    proof = (unpack_points(curve, 1, a)[0], unpack_points(curve, 2, b)[0], unpack_points(curve, 1, c)[0])
+    return pairing.groth16_verify(vk_pts, list(z_inst[1:]), proof)
