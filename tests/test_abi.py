@@ -44,3 +44,19 @@ def test_product_does_not_import_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp", ".hpp", ".sh")):
                 src = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle|#include\s+\"[^\"]*oracle", src, flags=re.M), (dirpath, f)
+
+
+def test_header_is_plain_c(tmp_path):
+    """The boundary is a C ABI: include/b200snark.h must compile as C99 and link against the library from C."""
+    import subprocess
+
+    src = tmp_path / "use.c"
+    src.write_text('#include "b200snark.h"\n#include <stdio.h>\n'
+                   "int main(void) { b2s_ctx* c = 0; int32_t st = b2s_ctx_create(B2S_CURVE_BN254, 0, &c);\n"
+                   '  printf("%s %d\\n", b2s_version(), (int)st); if (c) b2s_ctx_destroy(c); return 0; }\n')
+    exe = tmp_path / "use"
+    libdir = os.path.join(ROOT, "snark_b200")
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe),
+                           "-L", libdir, "-lb200snark", "-Wl,-rpath," + libdir])
+    out = subprocess.run([str(exe)], capture_output=True, text=True, timeout=60)
+    assert out.returncode == 0 and "b200snark" in out.stdout
