@@ -8,6 +8,7 @@ prover hot path and the in-tree matrix x witness products:
   * ConstraintSystem builder           relations/src/gr1cs/constraint_system.rs:109-139,323-353,
                                        472-532,591-617
   * finalize / inline_all_lcs          constraint_system.rs:691-758
+  * instance outlining                 constraint_system.rs:807-863, instance_outliner.rs:40-60
   * to_matrices / get_lc / make_row    constraint_system.rs:768-804, predicate/mod.rs:207-217
   * is_satisfied (R1CS: x0*x1 - x2)    predicate/mod.rs:115-120,185-204
   * mat_vec_mul                        relations/src/utils/matrix.rs:26-36
@@ -140,6 +141,7 @@ class ConstraintSystem:
         self.constraints = []                     # R1CS predicate: list of (a_var, b_var, c_var)
         # other predicates (predicate/mod.rs:81-94): label -> dict(arity, terms, constraints)
         self.predicates = {}
+        self.instance_outliner = None             # (pred_label, func) -- instance_outliner.rs:17-26
 
     # -- allocation (constraint_system.rs:591-617) ------------------------
     def new_input_variable(self, f):
@@ -223,8 +225,38 @@ class ConstraintSystem:
             out[label] = mats
         return dict(sorted(out.items()))
 
-    # -- finalize (constraint_system.rs:691-758) --------------------------
+    # -- finalize (constraint_system.rs:691-707) --------------------------
     def finalize(self):
+        self.inline_all_lcs()
+        if self.instance_outliner is not None:
+            label, func = self.instance_outliner
+            self.instance_outliner = None
+            if label == "R1CS" or label in self.predicates:
+                self.perform_instance_outlining(func)
+
+    def set_instance_outliner(self, pred_label, func):
+        """constraint_system.rs:807-809."""
+        self.instance_outliner = (pred_label, func)
+
+    def perform_instance_outlining(self, func):
+        """constraint_system.rs:826-863: a witness copy of ONE and of every instance variable; every stored LC is
+        rewritten to use the copies (bare single-variable constraint arguments are not LCs and stay as they are);
+        `func` then ties copies to instances."""
+        one_w = self.new_witness_variable(lambda: 1)
+        imap = [one_w]
+        inst = list(self.instance_assignment)
+        for i in range(1, self.num_instance_variables):
+            imap.append(self.new_witness_variable(lambda i=i: inst[i]))
+        for row in self.lcs:
+            for k, (c, v) in enumerate(row):
+                if v[0] == INSTANCE:
+                    row[k] = (c, imap[v[1]])
+                elif v[0] == ONE:
+                    row[k] = (c, one_w)
+        func(self, imap)
+
+    def inline_all_lcs(self):
+        """constraint_system.rs:717-758."""
         if not any(v[0] == LC for row in self.lcs for _, v in row):
             return
         inlined = []
@@ -298,6 +330,15 @@ class ConstraintSystem:
     def z(self):
         """instance || witness (sr1cs/mod.rs:199-200)."""
         return self.instance_assignment + self.witness_assignment
+
+
+def outline_r1cs(cs, instance_witness_map):
+    """instance_outliner.rs:40-60: one * one = One, then one * w_i = x_i for every instance variable."""
+    r = cs.r
+    one = instance_witness_map[0]
+    cs.enforce_r1cs_constraint(lc(r, one), lc(r, one), lc(r, V_ONE))
+    for i, w in list(enumerate(instance_witness_map))[1:]:
+        cs.enforce_r1cs_constraint(lc(r, one), lc(r, w), lc(r, instance(i)))
 
 
 # ---------------------------------------------------------------------------------------------

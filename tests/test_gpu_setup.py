@@ -32,6 +32,8 @@ def test_setup_matches_oracle_and_proves(be):
     cs = orc.circuit2(curve, 1, 1, 2); cs.finalize(); cases.append(("circuit2", cs))
     cases.append(("dummy", orc.dummy_circuit(curve, 3, 5, 16, 16)))
     bc = orc.bench_circuit(curve, 25, seed=9); bc.finalize(); cases.append(("bench25", bc))
+    # instance-outlined system (instance_outliner.rs:40-60): two extra rows, unsorted columns in the rewritten LCs
+    oc = orc.circuit2(curve, 1, 1, 2); oc.set_instance_outliner("R1CS", orc.outline_r1cs); oc.finalize(); cases.append(("circuit2-outlined", oc))
     for name, cs in cases:
         mats, inst, wit = cs.to_matrices(), cs.instance_assignment, cs.witness_assignment
         td = og.Trapdoor(*[rng.randrange(1, curve.r) for _ in range(5)])

@@ -58,6 +58,54 @@ def test_reference_golden_circuit1():
     assert not orc.circuit1(BLS12_381, *orc.CIRCUIT1_UNSAT).is_satisfied()
 
 
+def test_circuit1_instance_outlined():
+    """test_circuit1_instance_outlined (gr1cs/tests/mod.rs:105-131) + what outlining must preserve."""
+    cs = orc.circuit1(BLS12_381, (0,) * 5, (0,) * 8)
+    num_instance, prev_num_witness = cs.num_instance_variables, cs.num_witness_variables
+    cs.set_instance_outliner("R1CS", orc.outline_r1cs)
+    cs.finalize()
+    assert num_instance == cs.num_witness_variables - prev_num_witness
+    assert cs.instance_outliner is None                                  # taken by finalize (constraint_system.rs:699)
+    # an outliner naming an unregistered predicate is dropped silently (constraint_system.rs:701)
+    cs = orc.circuit2(BLS12_381, 1, 1, 2)
+    cs.set_instance_outliner("no-such-predicate", orc.outline_r1cs)
+    cs.finalize()
+    assert cs.num_witness_variables == 2 and cs.to_matrices() == orc.CIRCUIT2_GOLDEN
+
+
+def test_outlined_circuit2_semantics():
+    """After outline_r1cs the system has l more witnesses and l more constraints (one*one = One; one*w_i = x_i), stays
+    satisfied by the same instance, rejects a wrong one, and stored LCs no longer mention instance columns."""
+    r = BLS12_381.r
+    cs = orc.circuit2(BLS12_381, 1, 1, 2)
+    cs.set_instance_outliner("R1CS", orc.outline_r1cs)
+    cs.finalize()
+    ell = cs.num_instance_variables
+    assert (ell, cs.num_witness_variables, cs.num_constraints()) == (2, 4, 5)
+    assert cs.witness_assignment == [1, 2, 1, 1] and cs.is_satisfied()   # copies: one_w = 1, w(x1) = 1
+    A, B, C = cs.to_matrices()
+    # rows 0..2: LCs that were stored in lc_map lost their instance / One columns; bare variables (row 0: A = x1) keep them
+    assert A[0] == [(1, 1)] and B[1] == [(1, 5), (1, 2)] and C[2] == [(2, 5), (2, 2)]   # replaced in place: rows unsorted
+    assert A[2] == [(1, 0)]                                             # `lc!() + One` is a bare variable, not an LC
+    # the new rows: (one_w, one_w, One) and (one_w, w_x1, x1)
+    assert (A[3], B[3], C[3]) == ([(1, 4)], [(1, 4)], [(1, 0)])
+    assert (A[4], B[4], C[4]) == ([(1, 4)], [(1, 5)], [(1, 1)])
+    z = cs.z()
+    az, bz, cz = (orc.mat_vec_mul(r, M, z) for M in (A, B, C))
+    assert all(a * b % r == c for a, b, c in zip(az, bz, cz))
+    cs.instance_assignment[1] = 7                                        # the tie one*w = x now fails
+    assert cs.which_is_unsatisfied() == ("R1CS", 0)
+    # setup mode: same shape, closures never evaluated
+    st = orc.ConstraintSystem(BLS12_381, setup_mode=True)
+    v = st.new_input_variable(lambda: 1 / 0)
+    w = st.new_witness_variable(lambda: 1 / 0)
+    st.enforce_r1cs_constraint(orc.lc(r, v, w), orc.lc(r, w), orc.lc(r, v))
+    st.set_instance_outliner("R1CS", orc.outline_r1cs)
+    st.finalize()
+    assert (st.num_instance_variables, st.num_witness_variables, st.num_constraints()) == (2, 3, 3)
+    assert st.to_matrices()[0][0] == [(1, 4), (1, 2)]                   # x1 + w0 became w(x1) + w0, order kept
+
+
 def test_dummy_circuit_shapes():
     """DummyCircuit (sr1cs/mod.rs:296-317): builder output == the direct generator used at scale."""
     for curve in CURVES:
@@ -125,7 +173,9 @@ def test_window_rule_and_add_counts():
 @pytest.mark.parametrize("curve", CURVES, ids=lambda c: c.name)
 def test_groth16_known_trapdoor(curve):
     rng = random.Random(0xB2000003)
-    for cs in (orc.circuit2(curve, 1, 1, 2), orc.dummy_circuit(curve, 3, 5, 8, 8), orc.bench_circuit(curve, 6, seed=1)):
+    outlined = orc.circuit2(curve, 1, 1, 2)
+    outlined.set_instance_outliner("R1CS", orc.outline_r1cs)
+    for cs in (orc.circuit2(curve, 1, 1, 2), orc.dummy_circuit(curve, 3, 5, 8, 8), orc.bench_circuit(curve, 6, seed=1), outlined):
         cs.finalize()
         assert cs.is_satisfied()
         mats, inst, wit = cs.to_matrices(), cs.instance_assignment, cs.witness_assignment
