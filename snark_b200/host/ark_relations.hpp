@@ -4,7 +4,8 @@
 // synthesis and witness assignment exactly as the reference does"); this image has no Rust toolchain, so
 // the same interface is provided in C++ with the reference's names, argument meaning and error behaviour,
 // for hosts that are C++ and so that tests/native/host_relations_test.cpp can read like the reference's own
-// tests (relations/src/gr1cs/tests/mod.rs).  R1CS predicate only (what Groth16 consumes).
+// tests (relations/src/gr1cs/tests/mod.rs).  Generic polynomial predicates are supported as in the reference; Groth16
+// consumes the R1CS predicate's matrices.
 //
 //   Variable                          relations/src/utils/variable.rs:4-14,105-113,177-183
 //   LinearCombination, lc()           relations/src/utils/linear_combination.rs:15-38,53-82,174-211
@@ -15,6 +16,11 @@
 //   ConstraintSystemRef               relations/src/gr1cs/constraint_system_ref.rs:26-34,235-250,345-383
 //   ConstraintSynthesizer             relations/src/gr1cs/mod.rs:54-61
 //   Matrix, mat_vec_mul, transpose    relations/src/utils/matrix.rs:4-36
+//   PolynomialPredicate               relations/src/gr1cs/predicate/polynomial_constraint.rs:16-73
+//   PredicateConstraintSystem         relations/src/gr1cs/predicate/mod.rs:81-217
+//   InstanceOutliner, outline_*       relations/src/gr1cs/instance_outliner.rs:17-80; constraint_system.rs:807-863
+//   Namespace / ns                    relations/src/gr1cs/namespace.rs:9-52 (tracing spans are not mirrored)
+//   Sr1csAdapter                      relations/src/sr1cs/mod.rs:18-265
 //
 // F is any field type with zero()/one()/+/-/*/==/is_zero() -- in this repository b2s::Fp<...> compiled for the
 // host.  Coefficient arithmetic here is the builder's own (a handful of additions/multiplications per
@@ -24,6 +30,7 @@
 #include <array>
 #include <cstdint>
 #include <functional>
+#include <map>
 #include <memory>
 #include <optional>
 #include <stdexcept>
@@ -136,6 +143,42 @@ struct LinearCombination {   // linear_combination.rs:15
     LinearCombination operator-(const std::pair<F, Variable>& cv) const { return *this + std::make_pair(F::zero() - cv.first, cv.second); }
     LinearCombination operator-(const Variable& v) const { return *this - std::make_pair(F::one(), v); }
     LinearCombination operator*(const F& k) const { LinearCombination r = *this; for (auto& t : r.terms) t.first = t.first * k; return r; }
+    void negate_in_place() { for (auto& t : terms) t.first = F::zero() - t.first; }   // :163-166
+    LinearCombination operator-() const { LinearCombination r = *this; r.negate_in_place(); return r; }
+    // LC (+|-) LC: a merge of two variable-sorted term lists (linear_combination.rs:300-343 and the impls below it)
+    LinearCombination operator+(const LinearCombination& o) const {
+        if (o.terms.empty()) return *this;
+        if (terms.empty()) return o;
+        return merge(o, false);
+    }
+    LinearCombination operator-(const LinearCombination& o) const {
+        if (o.terms.empty()) return *this;
+        if (terms.empty()) return -o;
+        return merge(o, true);
+    }
+    // From<Variable> / From<(F, Variable)> (linear_combination.rs:126-147)
+    static LinearCombination from(const Variable& v) { return v.is_zero() ? LinearCombination() : LinearCombination({{F::one(), v}}); }
+    static LinearCombination from(const F& c, const Variable& v) { return (c.is_zero() || v.is_zero()) ? LinearCombination() : LinearCombination({{c, v}}); }
+    // lc_diff!(a, b) (linear_combination.rs:32-38, 107-113)
+    static LinearCombination diff_vars(const Variable& a, const Variable& b) {
+        if (a == b) return {};
+        return LinearCombination({{F::one(), a}, {F::zero() - F::one(), b}});
+    }
+
+private:
+    LinearCombination merge(const LinearCombination& o, bool subtract) const {
+        LinearCombination r;
+        size_t i = 0, j = 0;
+        auto other = [&](size_t k) { return subtract ? F::zero() - o.terms[k].first : o.terms[k].first; };
+        while (i < terms.size() && j < o.terms.size()) {
+            if (o.terms[j].second < terms[i].second) { r.terms.emplace_back(other(j), o.terms[j].second); j++; }
+            else if (terms[i].second < o.terms[j].second) r.terms.push_back(terms[i++]);
+            else { r.terms.emplace_back(subtract ? terms[i].first - o.terms[j].first : terms[i].first + o.terms[j].first, terms[i].second); i++; j++; }
+        }
+        for (; i < terms.size(); i++) r.terms.push_back(terms[i]);
+        for (; j < o.terms.size(); j++) r.terms.emplace_back(other(j), o.terms[j].second);
+        return r;
+    }
 };
 
 // lc!() forms (linear_combination.rs:19-30): lc<F>() empty; lc<F>({a, b}) = sum of variables; lc_pairs = sum of pairs
@@ -152,6 +195,8 @@ template <class F> LinearCombination<F> lc_pairs(std::initializer_list<std::pair
     r.compactify();
     return r;
 }
+
+template <class F> LinearCombination<F> lc_diff(const Variable& a, const Variable& b) { return LinearCombination<F>::diff_vars(a, b); }
 
 template <class F> using Matrix = std::vector<std::vector<std::pair<F, size_t>>>;   // utils/matrix.rs:4
 
@@ -180,6 +225,96 @@ struct SynthesisMode {   // gr1cs/mod.rs:75-90
 };
 enum class OptimizationGoal { None, Constraints, Weight };   // gr1cs/mod.rs:96-106
 
+using Label = std::string;
+inline const Label R1CS_PREDICATE_LABEL = "R1CS";     // polynomial_constraint.rs:68-69
+inline const Label SR1CS_PREDICATE_LABEL = "SR1CS";   // polynomial_constraint.rs:71-73
+
+template <class F> class ConstraintSystem;
+
+// A sparse multivariate polynomial; the predicate holds iff it evaluates to zero (polynomial_constraint.rs:16-66).
+// terms: (coefficient, [(argument index, exponent), ...]).
+template <class F>
+struct PolynomialPredicate {
+    using Monomial = std::vector<std::pair<size_t, size_t>>;
+    using Terms = std::vector<std::pair<F, Monomial>>;
+    size_t num_vars = 0;
+    Terms terms;
+    PolynomialPredicate() = default;
+    PolynomialPredicate(size_t arity, Terms t) : num_vars(arity), terms(std::move(t)) {}
+    F eval(const std::vector<F>& x) const {
+        if (x.size() < num_vars) throw std::logic_error("PolynomialPredicate::eval: too few arguments");
+        F acc = F::zero();
+        for (const auto& [coeff, mono] : terms) {
+            F t = coeff;
+            for (const auto& [var, power] : mono)
+                for (size_t k = 0; k < power; k++) t = t * x[var];
+            acc = acc + t;
+        }
+        return acc;
+    }
+    bool is_satisfied(const std::vector<F>& x) const { return eval(x).is_zero(); }
+    size_t arity() const { return num_vars; }
+    size_t degree() const {   // largest total degree of a term
+        size_t d = 0;
+        for (const auto& [coeff, mono] : terms) { size_t t = 0; for (const auto& vp : mono) t += vp.second; d = std::max(d, t); }
+        return d;
+    }
+};
+
+// The constraints enforced under one predicate, stored column-wise: argument_lcs[k][i] is the k-th argument of the
+// i-th constraint (predicate/mod.rs:81-94).
+template <class F>
+class PredicateConstraintSystem {
+public:
+    using Terms = typename PolynomialPredicate<F>::Terms;
+    static PredicateConstraintSystem new_polynomial_predicate_cs(size_t arity, Terms terms) {   // :108-112
+        PredicateConstraintSystem p;
+        p.predicate_ = PolynomialPredicate<F>(arity, std::move(terms));
+        p.argument_lcs_.assign(arity, {});
+        return p;
+    }
+    static PredicateConstraintSystem new_r1cs() {   // :116-121   x0 * x1 - x2
+        const F one = F::one(), minus_one = F::zero() - F::one();
+        return new_polynomial_predicate_cs(3, {{one, {{0, 1}, {1, 1}}}, {minus_one, {{2, 1}}}});
+    }
+    static PredicateConstraintSystem new_sr1cs_predicate() {   // :124-129   x0^2 - x1
+        const F one = F::one(), minus_one = F::zero() - F::one();
+        return new_polynomial_predicate_cs(2, {{one, {{0, 2}}}, {minus_one, {{1, 1}}}});
+    }
+    size_t get_arity() const { return predicate_.arity(); }
+    size_t num_constraints() const { return num_constraints_; }
+    const std::vector<std::vector<Variable>>& get_constraints() const { return argument_lcs_; }
+    const PolynomialPredicate<F>& get_predicate() const { return predicate_; }
+
+    // predicate/mod.rs:156-174.  As upstream: the arguments are zipped with the columns BEFORE the arity check, so a
+    // short list leaves its partial push behind and fails with ArityMismatch, and surplus arguments are dropped.
+    void enforce_constraint(const std::vector<Variable>& constraint) {
+        size_t arity = 0;
+        for (; arity < constraint.size() && arity < argument_lcs_.size(); arity++) argument_lcs_[arity].push_back(constraint[arity]);
+        if (arity != get_arity()) throw SynthesisFailure(SynthesisError::ArityMismatch);
+        num_constraints_++;
+    }
+    std::vector<Variable> constraint(size_t i) const {
+        std::vector<Variable> c;
+        for (const auto& col : argument_lcs_) c.push_back(col[i]);
+        return c;
+    }
+    std::optional<size_t> which_constraint_is_unsatisfied(const ConstraintSystem<F>& cs) const;   // :185-204
+    std::vector<Matrix<F>> to_matrices(const ConstraintSystem<F>& cs) const;                      // :207-217
+
+private:
+    std::vector<std::vector<Variable>> argument_lcs_;
+    size_t num_constraints_ = 0;
+    PolynomialPredicate<F> predicate_;
+};
+
+// instance_outliner.rs:17-26: which predicate ties the copies to the instances, and how.
+template <class F>
+struct InstanceOutliner {
+    Label pred_label;
+    std::function<void(ConstraintSystem<F>&, const std::vector<Variable>&)> func;
+};
+
 template <class F>
 class ConstraintSystem {
 public:
@@ -187,23 +322,45 @@ public:
     using Lazy = std::function<F()>;
     using LazyLc = std::function<LC()>;
 
-    ConstraintSystem() {   // constraint_system.rs:109-139
+    ConstraintSystem() {   // constraint_system.rs:109-139: One is instance 0, LC 0 is the empty LC, R1CS is registered
         instance_assignment_.push_back(F::one());
         lcs_.push_back({});
         lc_assignment_.push_back(F::zero());
+        register_predicate(R1CS_PREDICATE_LABEL, PredicateConstraintSystem<F>::new_r1cs());
     }
-    // -- counters (constraint_system.rs:210-230)
-    size_t num_constraints() const { return constraints_.size(); }
+    // -- counters (constraint_system.rs:210-236)
+    size_t num_constraints() const { size_t n = 0; for (const auto& kv : predicates_) n += kv.second.num_constraints(); return n; }
     size_t num_instance_variables() const { return num_instance_; }
     size_t num_witness_variables() const { return num_witness_; }
     size_t num_variables() const { return num_instance_ + num_witness_; }
+    size_t num_predicates() const { return predicates_.size(); }
+
+    // -- predicates (constraint_system.rs:146-191, 620-642)
+    void register_predicate(const Label& label, PredicateConstraintSystem<F> p) { predicates_.insert_or_assign(label, std::move(p)); }
+    void remove_predicate(const Label& label) { predicates_.erase(label); }
+    bool has_predicate(const Label& label) const { return predicates_.count(label) != 0; }
+    std::optional<size_t> get_predicate_num_constraints(const Label& label) const {
+        auto it = predicates_.find(label);
+        return it == predicates_.end() ? std::nullopt : std::optional<size_t>(it->second.num_constraints());
+    }
+    std::optional<size_t> get_predicate_arity(const Label& label) const {
+        auto it = predicates_.find(label);
+        return it == predicates_.end() ? std::nullopt : std::optional<size_t>(it->second.get_arity());
+    }
+    std::map<Label, size_t> get_all_predicates_num_constraints() const {
+        std::map<Label, size_t> m; for (const auto& kv : predicates_) m[kv.first] = kv.second.num_constraints(); return m;
+    }
+    std::map<Label, size_t> get_all_predicate_arities() const {
+        std::map<Label, size_t> m; for (const auto& kv : predicates_) m[kv.first] = kv.second.get_arity(); return m;
+    }
+    const std::map<Label, PredicateConstraintSystem<F>>& predicates() const { return predicates_; }
 
     void set_mode(SynthesisMode m) { mode_ = m; }
     bool is_in_setup_mode() const { return mode_.setup; }
     bool should_construct_matrices() const { return mode_.setup || mode_.construct_matrices; }
     bool should_generate_lc_assignments() const { return !mode_.setup && mode_.generate_lc_assignments; }
-    void set_optimization_goal(OptimizationGoal g) {   // :563-566 asserts is_new
-        if (!(num_instance_ == 1 && num_witness_ == 0 && constraints_.empty() && lcs_.size() == 1))
+    void set_optimization_goal(OptimizationGoal g) {   // :563-566 asserts is_new (:554-559)
+        if (!(num_instance_ == 1 && num_witness_ == 0 && num_constraints() == 0 && num_lcs_ == 1))
             throw std::logic_error("set_optimization_goal on a non-empty constraint system");
         goal_ = g;
     }
@@ -222,13 +379,23 @@ public:
     }
     Variable new_lc(const LazyLc& f) { return new_lc_helper(f); }   // :523-532
 
-    // -- constraints (constraint_system.rs:323-353, 431-438)
-    void enforce_r1cs_constraint(const LazyLc& a, const LazyLc& b, const LazyLc& c) {
-        if (should_construct_matrices()) {
-            Variable va = new_lc_helper(a), vb = new_lc_helper(b), vc = new_lc_helper(c);
-            constraints_.push_back({va, vb, vc});
-        }
+    // -- constraints (constraint_system.rs:241-451)
+    void enforce_constraint(const Label& label, const std::vector<LazyLc>& lcs) {
+        auto it = predicates_.find(label);
+        if (it == predicates_.end()) throw SynthesisFailure(SynthesisError::PredicateNotFound);
+        if (!should_construct_matrices()) return;
+        std::vector<Variable> args;
+        for (const auto& f : lcs) args.push_back(new_lc_helper(f));   // new_constraint_lc :455-461
+        it->second.enforce_constraint(args);
     }
+    void enforce_constraint_arity_2(const Label& l, const LazyLc& a, const LazyLc& b) { enforce_constraint(l, {a, b}); }
+    void enforce_constraint_arity_3(const Label& l, const LazyLc& a, const LazyLc& b, const LazyLc& c) { enforce_constraint(l, {a, b, c}); }
+    void enforce_constraint_arity_4(const Label& l, const LazyLc& a, const LazyLc& b, const LazyLc& c, const LazyLc& d) { enforce_constraint(l, {a, b, c, d}); }
+    void enforce_constraint_arity_5(const Label& l, const LazyLc& a, const LazyLc& b, const LazyLc& c, const LazyLc& d, const LazyLc& e) {
+        enforce_constraint(l, {a, b, c, d, e});
+    }
+    void enforce_r1cs_constraint(const LazyLc& a, const LazyLc& b, const LazyLc& c) { enforce_constraint_arity_3(R1CS_PREDICATE_LABEL, a, b, c); }
+    void enforce_sr1cs_constraint(const LazyLc& a, const LazyLc& b) { enforce_constraint_arity_2(SR1CS_PREDICATE_LABEL, a, b); }
 
     // -- assignments (constraint_system.rs:193-206)
     const std::vector<F>& instance_assignment() const {
@@ -248,9 +415,30 @@ public:
             default: return v.payload() < lc_assignment_.size() ? std::optional<F>(lc_assignment_[v.payload()]) : std::nullopt;
         }
     }
+    // value of a constraint argument: the stored assignment, else the LC evaluated term by term (predicate/mod.rs:190-197)
+    F argument_value(Variable v) const {
+        if (auto val = assigned_value(v)) return *val;
+        F acc = F::zero();
+        for (const auto& [c, u] : get_lc(v).terms) {
+            auto x = assigned_value(u);
+            if (!x) throw std::logic_error("variable is not assigned; did you run cs.finalize()?");
+            acc = acc + c * *x;
+        }
+        return acc;
+    }
 
-    // -- finalize: inline_all_lcs (constraint_system.rs:691-758)
+    // -- finalize (constraint_system.rs:691-707): inline, then outline the instances if asked to
     void finalize() {
+        inline_all_lcs();
+        if (instance_outliner_) {
+            InstanceOutliner<F> o = std::move(*instance_outliner_);
+            instance_outliner_.reset();
+            if (has_predicate(o.pred_label)) {
+                try { perform_instance_outlining(o); } catch (const SynthesisFailure&) {}   // `let _ =` upstream
+            }
+        }
+    }
+    void inline_all_lcs() {   // :717-758
         if (!should_construct_matrices()) return;
         bool any_used = false;
         for (const auto& l : lcs_) for (const auto& t : l) any_used |= t.second.is_lc();
@@ -275,10 +463,32 @@ public:
         lcs_ = std::move(inlined);
     }
 
-    // -- export (constraint_system.rs:768-804; predicate/mod.rs:207-217): [A, B, C]
+    // -- instance outlining (constraint_system.rs:807-863)
+    void set_instance_outliner(InstanceOutliner<F> o) { instance_outliner_ = std::move(o); }
+    bool should_outline_instances() const { return instance_outliner_.has_value(); }
+    void perform_instance_outlining(const InstanceOutliner<F>& outliner) {
+        std::vector<Variable> instance_to_witness;
+        const Variable one_witness = new_witness_variable([] { return F::one(); });
+        instance_to_witness.push_back(one_witness);
+        const std::vector<F> inst = instance_assignment_;
+        for (size_t i = 1; i < num_instance_; i++)
+            instance_to_witness.push_back(new_witness_variable([&] {
+                if (i >= inst.size()) throw SynthesisFailure(SynthesisError::AssignmentMissing);
+                return inst[i];
+            }));
+        // rewritten in place: the terms keep their positions, so rows may come out unsorted (the C ABI allows that)
+        for (auto& l : lcs_)
+            for (auto& t : l) {
+                if (t.second.is_instance()) t.second = instance_to_witness[t.second.payload()];
+                else if (t.second.is_one()) t.second = one_witness;
+            }
+        outliner.func(*this, instance_to_witness);
+    }
+
+    // -- export (constraint_system.rs:768-804): label -> one matrix per predicate argument
     LC get_lc(Variable v) const {
         if (v.is_zero()) return {};
-        if (v.is_lc()) return LC(lcs_[v.payload()]);
+        if (v.is_lc()) return LC(lcs_.at(v.payload()));
         return LC({{F::one(), v}});
     }
     std::vector<std::pair<F, size_t>> make_row(const LC& l) const {
@@ -289,42 +499,30 @@ public:
         }
         return row;
     }
-    std::vector<Matrix<F>> to_matrices() const {
-        std::vector<Matrix<F>> m(3);
-        for (const auto& cons : constraints_)
-            for (int k = 0; k < 3; k++) m[k].push_back(make_row(get_lc(cons[k])));
+    std::map<Label, std::vector<Matrix<F>>> to_matrices() const {
+        std::map<Label, std::vector<Matrix<F>>> m;
+        for (const auto& kv : predicates_) m[kv.first] = kv.second.to_matrices(*this);
         return m;
     }
 
-    // -- satisfaction (constraint_system.rs:652-687; predicate/mod.rs:185-204), R1CS: x0*x1 - x2 == 0
-    std::optional<size_t> which_is_unsatisfied() const {
+    // -- satisfaction (constraint_system.rs:652-687): "<label> - <index>" of the first failing constraint, predicates
+    // visited in label order (the form upstream reports when no ConstraintLayer trace is installed)
+    std::optional<std::string> which_is_unsatisfied() const {
         if (is_in_setup_mode()) throw SynthesisFailure(SynthesisError::AssignmentMissing);
-        for (size_t i = 0; i < constraints_.size(); i++) {
-            F x[3];
-            for (int k = 0; k < 3; k++) {
-                Variable v = constraints_[i][k];
-                auto val = assigned_value(v);
-                if (!val) {
-                    F acc = F::zero();
-                    for (const auto& [c, u] : get_lc(v).terms) acc = acc + c * *assigned_value(u);
-                    val = acc;
-                }
-                x[k] = *val;
-            }
-            if (!(x[0] * x[1] - x[2]).is_zero()) return i;
-        }
+        for (const auto& kv : predicates_)
+            if (auto i = kv.second.which_constraint_is_unsatisfied(*this)) return kv.first + " - " + std::to_string(*i);
         return std::nullopt;
     }
     bool is_satisfied() const { return !which_is_unsatisfied().has_value(); }
 
 private:
     Variable new_lc_helper(const LazyLc& f) {   // constraint_system.rs:472-519
-        if (!(should_construct_matrices() || should_generate_lc_assignments())) return Variable::symbolic_lc(lcs_.size());
+        if (!(should_construct_matrices() || should_generate_lc_assignments())) return Variable::symbolic_lc(num_lcs_++);   // :465-469
         LC l = f();
         const auto& t = l.terms;
         if (t.empty() || (t.size() == 1 && t[0].second.is_zero())) return Variable::symbolic_lc(0);
         if (t.size() == 1 && t[0].first == F::one()) return t[0].second;
-        size_t idx = lcs_.size();
+        size_t idx = num_lcs_++;
         lcs_.push_back(t);
         if (should_generate_lc_assignments()) {   // assignment.rs:40-52
             F acc = F::zero();
@@ -334,40 +532,111 @@ private:
         return Variable::symbolic_lc(idx);
     }
 
-    size_t num_instance_ = 1, num_witness_ = 0;
+    size_t num_instance_ = 1, num_witness_ = 0, num_lcs_ = 1;
     std::vector<F> instance_assignment_, witness_assignment_, lc_assignment_;
     std::vector<std::vector<std::pair<F, Variable>>> lcs_;
-    std::vector<std::array<Variable, 3>> constraints_;
+    std::map<Label, PredicateConstraintSystem<F>> predicates_;   // BTreeMap upstream: iteration in label order
+    std::optional<InstanceOutliner<F>> instance_outliner_;
     SynthesisMode mode_ = SynthesisMode::Prove(true, true);   // constraint_system.rs:128-131
     OptimizationGoal goal_ = OptimizationGoal::None;
 };
+
+template <class F>
+std::optional<size_t> PredicateConstraintSystem<F>::which_constraint_is_unsatisfied(const ConstraintSystem<F>& cs) const {
+    std::vector<F> x(argument_lcs_.size(), F::zero());
+    for (size_t i = 0; i < num_constraints_; i++) {
+        for (size_t k = 0; k < argument_lcs_.size(); k++) x[k] = cs.argument_value(argument_lcs_[k][i]);
+        if (!predicate_.is_satisfied(x)) return i;
+    }
+    return std::nullopt;
+}
+template <class F>
+std::vector<Matrix<F>> PredicateConstraintSystem<F>::to_matrices(const ConstraintSystem<F>& cs) const {
+    std::vector<Matrix<F>> m(get_arity());
+    for (size_t i = 0; i < num_constraints_; i++)
+        for (size_t k = 0; k < argument_lcs_.size(); k++) m[k].push_back(cs.make_row(cs.get_lc(argument_lcs_[k][i])));
+    return m;
+}
+
+// instance_outliner.rs:40-60: one_w * one_w = One, then one_w * w_i = x_i for every instance variable
+template <class F>
+void outline_r1cs(ConstraintSystem<F>& cs, const std::vector<Variable>& instance_witness_map) {
+    const Variable one = instance_witness_map[0];
+    cs.enforce_r1cs_constraint([&] { return lc<F>({one}); }, [&] { return lc<F>({one}); }, [&] { return lc<F>({Variable::One()}); });
+    for (size_t i = 1; i < instance_witness_map.size(); i++) {
+        const Variable w = instance_witness_map[i];
+        cs.enforce_r1cs_constraint([&] { return lc<F>({one}); }, [&] { return lc<F>({w}); }, [&] { return lc<F>({Variable::instance(i)}); });
+    }
+}
+// instance_outliner.rs:63-80: (x_i - w_i)^2 = 0 for every instance variable, the constant included
+template <class F>
+void outline_sr1cs(ConstraintSystem<F>& cs, const std::vector<Variable>& instance_witness_map) {
+    for (size_t i = 0; i < instance_witness_map.size(); i++) {
+        const Variable w = instance_witness_map[i];
+        cs.enforce_sr1cs_constraint([&] { return lc_diff<F>(Variable::instance(i), w); }, [] { return lc<F>(); });
+    }
+}
 
 // Shared handle with a `None` variant (constraint_system_ref.rs:26-34).
 template <class F>
 class ConstraintSystemRef {
 public:
+    using CS = ConstraintSystem<F>;
     ConstraintSystemRef() = default;   // None
-    static ConstraintSystemRef new_ref() { ConstraintSystemRef r; r.cs_ = std::make_shared<ConstraintSystem<F>>(); return r; }
+    static ConstraintSystemRef new_ref() { ConstraintSystemRef r; r.cs_ = std::make_shared<CS>(); return r; }
     bool is_none() const { return !cs_; }
-    ConstraintSystem<F>& inner() const { if (!cs_) throw SynthesisFailure(SynthesisError::MissingCS); return *cs_; }
-    ConstraintSystem<F>* operator->() const { return &inner(); }
-    Variable new_input_variable(const typename ConstraintSystem<F>::Lazy& f) const { return inner().new_input_variable(f); }
-    Variable new_witness_variable(const typename ConstraintSystem<F>::Lazy& f) const { return inner().new_witness_variable(f); }
-    Variable new_lc(const typename ConstraintSystem<F>::LazyLc& f) const { return inner().new_lc(f); }
-    // constraint_system_ref.rs:235-250: a no-op returning Ok when matrices are not being constructed
-    void enforce_r1cs_constraint(const typename ConstraintSystem<F>::LazyLc& a, const typename ConstraintSystem<F>::LazyLc& b,
-                                 const typename ConstraintSystem<F>::LazyLc& c) const { inner().enforce_r1cs_constraint(a, b, c); }
-    void finalize() const { inner().finalize(); }
+    ConstraintSystemRef or_(const ConstraintSystemRef& other) const { return is_none() ? other : *this; }   // :457-462
+    CS& inner() const { if (!cs_) throw SynthesisFailure(SynthesisError::MissingCS); return *cs_; }
+    CS* operator->() const { return &inner(); }
+    Variable new_input_variable(const typename CS::Lazy& f) const { return inner().new_input_variable(f); }
+    Variable new_witness_variable(const typename CS::Lazy& f) const { return inner().new_witness_variable(f); }
+    Variable new_lc(const typename CS::LazyLc& f) const { return inner().new_lc(f); }
+    // constraint_system_ref.rs:144-270: no-ops returning Ok when matrices are not being constructed
+    void enforce_constraint(const Label& l, const std::vector<typename CS::LazyLc>& lcs) const { inner().enforce_constraint(l, lcs); }
+    void enforce_constraint_arity_2(const Label& l, const typename CS::LazyLc& a, const typename CS::LazyLc& b) const { inner().enforce_constraint_arity_2(l, a, b); }
+    void enforce_constraint_arity_3(const Label& l, const typename CS::LazyLc& a, const typename CS::LazyLc& b, const typename CS::LazyLc& c) const {
+        inner().enforce_constraint_arity_3(l, a, b, c);
+    }
+    void enforce_constraint_arity_4(const Label& l, const typename CS::LazyLc& a, const typename CS::LazyLc& b, const typename CS::LazyLc& c,
+                                    const typename CS::LazyLc& d) const { inner().enforce_constraint_arity_4(l, a, b, c, d); }
+    void enforce_constraint_arity_5(const Label& l, const typename CS::LazyLc& a, const typename CS::LazyLc& b, const typename CS::LazyLc& c,
+                                    const typename CS::LazyLc& d, const typename CS::LazyLc& e) const { inner().enforce_constraint_arity_5(l, a, b, c, d, e); }
+    void enforce_r1cs_constraint(const typename CS::LazyLc& a, const typename CS::LazyLc& b, const typename CS::LazyLc& c) const { inner().enforce_r1cs_constraint(a, b, c); }
+    void enforce_sr1cs_constraint(const typename CS::LazyLc& a, const typename CS::LazyLc& b) const { inner().enforce_sr1cs_constraint(a, b); }
+    void register_predicate(const Label& l, PredicateConstraintSystem<F> p) const { inner().register_predicate(l, std::move(p)); }
+    void remove_predicate(const Label& l) const { inner().remove_predicate(l); }
+    bool has_predicate(const Label& l) const { return cs_ && cs_->has_predicate(l); }   // :403-406
+    size_t num_predicates() const { return inner().num_predicates(); }
+    void finalize() const { if (cs_) cs_->finalize(); }                 // :435-439: None is a no-op
+    void inline_all_lcs() const { if (cs_) cs_->inline_all_lcs(); }
     bool is_satisfied() const { return inner().is_satisfied(); }
-    std::vector<Matrix<F>> to_matrices() const { return inner().to_matrices(); }
+    std::optional<std::string> which_is_unsatisfied() const { return inner().which_is_unsatisfied(); }
+    std::optional<F> assigned_value(Variable v) const { return cs_ ? cs_->assigned_value(v) : std::nullopt; }
+    std::map<Label, std::vector<Matrix<F>>> to_matrices() const { return inner().to_matrices(); }
     size_t num_constraints() const { return inner().num_constraints(); }
     size_t num_instance_variables() const { return inner().num_instance_variables(); }
     size_t num_witness_variables() const { return inner().num_witness_variables(); }
+    size_t num_variables() const { return inner().num_variables(); }
     void set_mode(SynthesisMode m) const { inner().set_mode(m); }
+    bool is_in_setup_mode() const { return cs_ && cs_->is_in_setup_mode(); }
+    bool should_construct_matrices() const { return cs_ && cs_->should_construct_matrices(); }
     void set_optimization_goal(OptimizationGoal g) const { inner().set_optimization_goal(g); }
+    OptimizationGoal optimization_goal() const { return cs_ ? cs_->optimization_goal() : OptimizationGoal::Constraints; }   // :305-309
+    void set_instance_outliner(InstanceOutliner<F> o) const { inner().set_instance_outliner(std::move(o)); }
+    bool should_outline_instances() const { return cs_ && cs_->should_outline_instances(); }
 private:
-    std::shared_ptr<ConstraintSystem<F>> cs_;
+    std::shared_ptr<CS> cs_;
 };
+
+// namespace.rs:9-52.  Upstream a namespace is a tracing span around a clone of the handle; the span is not mirrored.
+template <class F>
+struct Namespace {
+    ConstraintSystemRef<F> inner;
+    std::string name;
+    ConstraintSystemRef<F> cs() const { return inner; }
+    void leave_namespace() {}
+};
+template <class F> Namespace<F> ns(const ConstraintSystemRef<F>& cs, std::string name) { return {cs, std::move(name)}; }
 
 // gr1cs/mod.rs:54-61
 template <class F>
@@ -377,4 +646,100 @@ struct ConstraintSynthesizer {
 };
 
 }  // namespace gr1cs
+
+// R1CS -> Square-R1CS (the Groth-Maller17 shape), relations/src/sr1cs/mod.rs:18-265.  a*b = c becomes
+// (a + b)^2 = 4c + s and (a - b)^2 = s with one fresh witness s per row; the old instance variables become
+// witnesses and are tied to fresh instance variables by (x_old - x_new)^2 = 0.
+namespace sr1cs {
+using namespace gr1cs;
+
+template <class F>
+struct Sr1csAdapter {
+    using Row = std::vector<std::pair<F, size_t>>;
+    using LC = LinearCombination<F>;
+
+    // sr1cs/mod.rs:24-56: inner product of a matrix row with the assignment; no multiplication for unit coefficients
+    static F evaluate_constraint(const Row& terms, const std::vector<F>& assignment) {
+        const F one = F::one();
+        F sum = F::zero();
+        for (const auto& [coeff, index] : terms) sum = sum + (coeff == one ? assignment[index] : assignment[index] * coeff);
+        return sum;
+    }
+
+    // :122-184 -- shape only (Setup mode); needs a system whose only predicate is R1CS
+    static ConstraintSystemRef<F> r1cs_to_sr1cs(const ConstraintSystemRef<F>& cs) {
+        if (cs.num_predicates() != 1) throw std::logic_error("r1cs_to_sr1cs: exactly one predicate expected");
+        return convert(cs.inner(), false);
+    }
+    // :192-264 -- with the assignment carried over; the result is finalized
+    static ConstraintSystemRef<F> r1cs_to_sr1cs_with_assignment(ConstraintSystem<F>& cs) {
+        auto out = convert(cs, true);
+        cs.set_mode(SynthesisMode::Prove(true, true));
+        out.finalize();
+        return out;
+    }
+
+private:
+    static ConstraintSystemRef<F> convert(ConstraintSystem<F>& cs, bool with_assignment) {
+        const auto all = cs.to_matrices();
+        const auto& m = all.at(R1CS_PREDICATE_LABEL);
+        const size_t num_public = cs.num_instance_variables();
+        std::vector<F> z;
+        if (with_assignment) {
+            z = cs.instance_assignment();
+            z.insert(z.end(), cs.witness_assignment().begin(), cs.witness_assignment().end());
+        }
+        auto out = ConstraintSystemRef<F>::new_ref();
+        out.remove_predicate(R1CS_PREDICATE_LABEL);
+        out.register_predicate(SR1CS_PREDICATE_LABEL, PredicateConstraintSystem<F>::new_sr1cs_predicate());
+        if (with_assignment) out.set_optimization_goal(OptimizationGoal::Constraints);
+        else out.set_mode(SynthesisMode::Setup());
+        std::map<size_t, Variable> public_vars, witness_vars;   // old column -> new witness, in order of first use
+        const F one = F::one();
+        auto value_of = [&](size_t col) { return with_assignment ? z[col] : one; };
+        // a row of the old matrix as an LC over the new variables, with its value
+        auto translate = [&](const Row& row) {
+            std::pair<LC, F> r{LC(), F::zero()};
+            for (const auto& term : row) {
+                const F coeff = term.first;
+                const size_t col = term.second;
+                Variable v = Variable::One();
+                if (col != 0) {
+                    auto& table = col < num_public ? public_vars : witness_vars;
+                    auto it = table.find(col);
+                    if (it == table.end()) it = table.emplace(col, out.new_witness_variable([&] { return value_of(col); })).first;
+                    v = it->second;
+                }
+                r.first.terms.emplace_back(coeff, v);   // collected as is: neither sorted nor merged upstream
+                r.second = r.second + coeff * value_of(col);
+            }
+            return r;
+        };
+        for (size_t i = 0; i < m[0].size() && i < m[1].size() && i < m[2].size(); i++) {
+            auto [a, a_val] = translate(m[0][i]);
+            auto [b, b_val] = translate(m[1][i]);
+            auto [c, c_val] = translate(m[2][i]);
+            (void)c_val;
+            const F d = a_val - b_val;
+            const Variable square = out.new_witness_variable([&] { return with_assignment ? d * d : one; });
+            for (auto& t : c.terms) { t.first = t.first + t.first; t.first = t.first + t.first; }
+            const LC a_lc = a, b_lc = b, c_lc = c;
+            out.enforce_sr1cs_constraint([&] { return a_lc + b_lc; }, [&] { return c_lc + square; });
+            out.enforce_sr1cs_constraint([&] { return a_lc - b_lc; }, [&] { return lc<F>({square}); });
+        }
+        for (const auto& kv : public_vars) {
+            const Variable old_var = kv.second;
+            F value = one;
+            if (with_assignment) {
+                auto v = out.assigned_value(old_var);
+                if (!v) throw SynthesisFailure(SynthesisError::AssignmentMissing);
+                value = *v;
+            }
+            const Variable new_var = out.new_input_variable([&] { return value; });
+            out.enforce_sr1cs_constraint([&] { return lc_diff<F>(old_var, new_var); }, [] { return lc<F>(); });
+        }
+        return out;
+    }
+};
+}  // namespace sr1cs
 }  // namespace ark_relations

@@ -129,7 +129,10 @@ private:
     // Matrix<F> (to_matrices(), constraint_system.rs:768-774) -> CSR -> device (once per circuit in a long-lived
     // prover; per call in this thin mirror)
     b2s_r1cs* upload_matrices(const ConstraintSystemRef<F>& cs) {
-        const auto mats = cs.to_matrices();
+        const auto all = cs.to_matrices();   // BTreeMap<Label, Vec<Matrix>> upstream; Groth16 takes the R1CS entry
+        const auto it = all.find(ark_relations::gr1cs::R1CS_PREDICATE_LABEL);
+        if (it == all.end() || it->second.size() != 3) throw BackendError(B2S_ERR_INVALID_ARG, "constraint system has no R1CS predicate");
+        const auto& mats = it->second;
         std::vector<uint64_t> rp[3];
         std::vector<uint32_t> col[3];
         std::vector<F> co[3];
@@ -144,7 +147,7 @@ private:
         const uint32_t* colp[3] = {col[0].data(), col[1].data(), col[2].data()};
         const void* cop[3] = {co[0].data(), co[1].data(), co[2].data()};
         b2s_r1cs* mat = nullptr;
-        check(b2s_r1cs_upload(ctx_, cs.num_constraints(), cs.num_instance_variables(), cs.num_witness_variables(), rpp, colp, cop, &mat));
+        check(b2s_r1cs_upload(ctx_, mats[0].size(), cs.num_instance_variables(), cs.num_witness_variables(), rpp, colp, cop, &mat));
         return mat;
     }
     void check(int32_t st) { if (st != B2S_OK) throw BackendError(st, b2s_last_error(ctx_)); }

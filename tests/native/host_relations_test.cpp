@@ -1,5 +1,5 @@
 // Tests of the C++ host mirror (snark_b200/host/*.hpp), written after the reference's own unit tests
-// (/root/reference/relations/src/gr1cs/tests/mod.rs, circuit2.rs, sr1cs/mod.rs:276-330, variable.rs:206-266).
+// (/root/reference/relations/src/gr1cs/tests/mod.rs, circuit1.rs, circuit2.rs, sr1cs/mod.rs:276-330, variable.rs:206-266).
 //   ./host_relations_test cpu            -> builder tests, no GPU
 //   ./host_relations_test gpu <curve> <circuit> tau alpha beta gamma delta r s   -> setup + prove through the C ABI, prints the proof
 #include <cstdio>
@@ -9,6 +9,49 @@
 #include "../../snark_b200/host/ark_snark.hpp"
 
 using namespace ark_relations::gr1cs;
+using ark_relations::sr1cs::Sr1csAdapter;
+
+template <class F>
+struct Circuit1 : ConstraintSynthesizer<F> {   // gr1cs/tests/circuit1.rs:10-24, 63-164
+    F x[5], w[8];
+    Circuit1(const F (&x_)[5], const F (&w_)[8]) { for (int i = 0; i < 5; i++) x[i] = x_[i]; for (int i = 0; i < 8; i++) w[i] = w_[i]; }
+    void generate_constraints(ConstraintSystemRef<F> cs) override {
+        auto input_ns = ns(cs, "Input variables");
+        Variable xv[5], wv[8];
+        for (int i = 0; i < 5; i++) xv[i] = input_ns.cs().new_input_variable([&, i] { return x[i]; });
+        ns(cs, "Witness variables");
+        for (int i = 0; i < 8; i++) wv[i] = cs.new_witness_variable([&, i] { return w[i]; });
+        const F one = F::one(), minus_one = F::zero() - one, three = one + one + one, seven = three + three + one;
+        cs.register_predicate("poly-predicate-A", PredicateConstraintSystem<F>::new_polynomial_predicate_cs(
+                                                      4, {{one, {{0, 1}, {1, 1}}}, {three, {{2, 2}}}, {minus_one, {{3, 1}}}}));
+        cs.register_predicate("poly-predicate-B", PredicateConstraintSystem<F>::new_polynomial_predicate_cs(
+                                                      3, {{seven, {{1, 1}}}, {one, {{0, 3}}}, {minus_one, {{2, 1}}}}));
+        cs.register_predicate("poly-predicate-C", PredicateConstraintSystem<F>::new_polynomial_predicate_cs(
+                                                      3, {{one, {{0, 1}, {1, 1}}}, {minus_one, {{2, 1}}}}));
+        auto V = [](Variable v) { return [v] { return lc<F>() + v; }; };
+        const Variable x1 = xv[0], x2 = xv[1], x3 = xv[2], x4 = xv[3], x5 = xv[4];
+        const Variable w1 = wv[0], w2 = wv[1], w3 = wv[2], w4 = wv[3], w5 = wv[4], w6 = wv[5], w8 = wv[7];
+        ns(cs, "Predicate A constraints");
+        cs.enforce_constraint_arity_4("poly-predicate-A", V(x1), V(x2), V(x3), V(w4));
+        ns(cs, "Predicate B constraints");
+        cs.enforce_constraint_arity_3("poly-predicate-B", V(x4), V(w1), V(w5));
+        cs.enforce_constraint_arity_3("poly-predicate-B", V(w5), V(w6), V(w8));
+        ns(cs, "Predicate C constraints");
+        cs.enforce_constraint_arity_3("poly-predicate-C", V(w2), V(w3), V(w6));
+        cs.enforce_constraint_arity_3("poly-predicate-C", [=] { return lc<F>() + w5 + w4; }, V(w8), V(x5));
+    }
+    static std::map<Label, std::vector<Matrix<F>>> get_matrices() {   // circuit1.rs:28-61
+        using Row = std::vector<std::pair<F, size_t>>;
+        const F one = F::one();
+        auto R = [&](size_t col) { return Row{{one, col}}; };
+        std::map<Label, std::vector<Matrix<F>>> m;
+        m[R1CS_PREDICATE_LABEL] = {{}, {}, {}};
+        m["poly-predicate-A"] = {{R(1)}, {R(2)}, {R(3)}, {R(9)}};
+        m["poly-predicate-B"] = {{R(4), R(10)}, {R(6), R(11)}, {R(10), R(13)}};
+        m["poly-predicate-C"] = {{R(7), Row{{one, 9}, {one, 10}}}, {R(8), R(13)}, {R(11), R(5)}};
+        return m;
+    }
+};
 
 template <class F>
 struct Circuit2 : ConstraintSynthesizer<F> {   // gr1cs/tests/circuit2.rs:47-60
@@ -65,7 +108,8 @@ static void cpu_tests(const char* name) {
             {Row{{two, 2}}, Row{{one, 1}, {one, 2}}, Row{{two, 1}, {two, 2}}},
             {Row{{one, 3}}, Row{{one, 1}, {one, 2}}, Row{{two, 1}, {two, 2}}},
         };
-        CHECK(cs.to_matrices() == golden);
+        CHECK(cs.to_matrices().at(R1CS_PREDICATE_LABEL) == golden);
+        CHECK(cs.to_matrices().size() == 1 && cs.num_predicates() == 1);
         CHECK(cs.is_satisfied());
         CHECK(cs.num_constraints() == 3 && cs.num_instance_variables() == 2 && cs.num_witness_variables() == 2);
         std::vector<F> z = cs->instance_assignment();
@@ -80,7 +124,7 @@ static void cpu_tests(const char* name) {
         auto cs = ConstraintSystemRef<F>::new_ref();
         c.generate_constraints(cs);
         CHECK(!cs.is_satisfied());
-        CHECK(cs->which_is_unsatisfied().value() == 0);
+        CHECK(cs.which_is_unsatisfied().value() == "R1CS - 0");
     }
     {   // r1cs_to_sr1cs test's DummyCircuit{128,128} synthesizes (sr1cs/mod.rs:320-330); shape checks
         DummyCircuit<F> c(U(3), U(5), 128, 128);
@@ -88,7 +132,7 @@ static void cpu_tests(const char* name) {
         c.generate_constraints(cs);
         CHECK(cs.num_constraints() == 128 && cs.num_instance_variables() == 2 && cs.num_witness_variables() == 127);
         CHECK(cs.is_satisfied());
-        auto m = cs.to_matrices();
+        auto m = cs.to_matrices().at(R1CS_PREDICATE_LABEL);
         CHECK(m[0][0].size() == 1 && m[0][0][0].second == 2 && m[1][0][0].second == 3 && m[2][0][0].second == 1);
         CHECK(m[0][127].empty() && m[1][127].empty() && m[2][127].empty());
     }
@@ -120,6 +164,133 @@ static void cpu_tests(const char* name) {
         CHECK(l.len() == 2);
         l.compactify();
         CHECK(l.len() == 1 && l.terms[0].first == two);
+    }
+    auto U32 = [&](uint64_t v) { return U(v); };
+    const F sat_x[5] = {U32(1), U32(2), U32(3), U32(0), U32(1255254)};
+    const F sat_w[8] = {U32(4), U32(2), U32(5), U32(29), U32(28), U32(10), U32(57), U32(22022)};
+    const F zeros5[5] = {F::zero(), F::zero(), F::zero(), F::zero(), F::zero()};
+    const F zeros8[8] = {F::zero(), F::zero(), F::zero(), F::zero(), F::zero(), F::zero(), F::zero(), F::zero()};
+    {   // test_circuit1_sat (tests/mod.rs:17-45): satisfied with and without the Constraints optimisation goal
+        Circuit1<F> c(sat_x, sat_w);
+        auto cs = ConstraintSystemRef<F>::new_ref();
+        c.generate_constraints(cs);
+        cs.finalize();
+        CHECK(cs.is_satisfied());
+        auto cs2 = ConstraintSystemRef<F>::new_ref();
+        cs2.set_optimization_goal(OptimizationGoal::Constraints);
+        c.generate_constraints(cs2);
+        cs2.finalize();
+        CHECK(cs2.is_satisfied());
+        CHECK(cs.num_constraints() == 5 && cs.num_predicates() == 4 && cs.num_instance_variables() == 6 && cs.num_witness_variables() == 8);
+        CHECK(cs->get_predicate_arity("poly-predicate-A").value() == 4 && cs->get_predicate_num_constraints("poly-predicate-B").value() == 2);
+        CHECK(!cs->get_predicate_arity("nope").has_value());
+        CHECK(cs->predicates().at("poly-predicate-B").get_predicate().degree() == 3);
+    }
+    {   // test_circuit1_non_sat (tests/mod.rs:47-76): x1 = 4 breaks predicate A; reported without finalize
+        F bad_x[5] = {U32(4), sat_x[1], sat_x[2], sat_x[3], sat_x[4]};
+        Circuit1<F> c(bad_x, sat_w);
+        auto cs = ConstraintSystemRef<F>::new_ref();
+        c.generate_constraints(cs);
+        CHECK(!cs.is_satisfied());
+        CHECK(cs.which_is_unsatisfied().value() == "poly-predicate-A - 0");
+    }
+    {   // test_circuit1_matrices (tests/mod.rs:78-103): golden map of circuit1.rs:28-61, BEFORE finalize
+        Circuit1<F> c(zeros5, zeros8);
+        auto cs = ConstraintSystemRef<F>::new_ref();
+        c.generate_constraints(cs);
+        CHECK(Circuit1<F>::get_matrices() == cs.to_matrices());
+        cs.set_instance_outliner({R1CS_PREDICATE_LABEL, outline_r1cs<F>});
+        cs.finalize();
+    }
+    {   // test_circuit1_instance_outlined (tests/mod.rs:105-131)
+        Circuit1<F> c(zeros5, zeros8);
+        auto cs = ConstraintSystemRef<F>::new_ref();
+        c.generate_constraints(cs);
+        const size_t num_instance = cs.num_instance_variables(), prev_num_witness = cs.num_witness_variables();
+        cs.set_instance_outliner({R1CS_PREDICATE_LABEL, outline_r1cs<F>});
+        CHECK(cs.should_outline_instances());
+        cs.finalize();
+        CHECK(num_instance == cs.num_witness_variables() - prev_num_witness);
+        CHECK(!cs.should_outline_instances());
+        CHECK(cs->get_predicate_num_constraints(R1CS_PREDICATE_LABEL).value() == num_instance);   // one tie per instance column
+    }
+    {   // what outlining does to circuit2: stored LCs lose their instance columns, two tie rows, still satisfied
+        Circuit2<F> c(one, one, two);
+        auto cs = ConstraintSystemRef<F>::new_ref();
+        c.generate_constraints(cs);
+        cs.set_instance_outliner({R1CS_PREDICATE_LABEL, outline_r1cs<F>});
+        cs.finalize();
+        using Row = std::vector<std::pair<F, size_t>>;
+        auto m = cs.to_matrices().at(R1CS_PREDICATE_LABEL);
+        CHECK(cs.num_witness_variables() == 4 && cs.num_constraints() == 5 && cs.is_satisfied());
+        CHECK((m[1][1] == Row{{one, 5}, {one, 2}}) && (m[2][2] == Row{{two, 5}, {two, 2}}));   // rewritten in place: unsorted
+        CHECK((m[0][3] == Row{{one, 4}}) && (m[1][3] == Row{{one, 4}}) && (m[2][3] == Row{{one, 0}}));
+        CHECK((m[0][4] == Row{{one, 4}}) && (m[1][4] == Row{{one, 5}}) && (m[2][4] == Row{{one, 1}}));
+        // an outliner naming an unregistered predicate is dropped (constraint_system.rs:701)
+        auto cs2 = ConstraintSystemRef<F>::new_ref();
+        c.generate_constraints(cs2);
+        cs2.set_instance_outliner({"no-such-predicate", outline_r1cs<F>});
+        cs2.finalize();
+        CHECK(cs2.num_witness_variables() == 2 && !cs2.should_outline_instances());
+    }
+    {   // predicate errors: unknown label, arity quirk of predicate/mod.rs:156-174
+        auto cs = ConstraintSystemRef<F>::new_ref();
+        Variable v = cs.new_witness_variable([&] { return one; });
+        auto L = [v] { return lc<F>() + v; };
+        bool threw = false;
+        try { cs.enforce_constraint_arity_2("missing", L, L); } catch (const SynthesisFailure& e) { threw = e.kind == SynthesisError::PredicateNotFound; }
+        CHECK(threw);
+        threw = false;
+        try { cs.enforce_constraint_arity_2(R1CS_PREDICATE_LABEL, L, L); } catch (const SynthesisFailure& e) { threw = e.kind == SynthesisError::ArityMismatch; }
+        CHECK(threw && cs.num_constraints() == 0);
+        CHECK(cs->predicates().at(R1CS_PREDICATE_LABEL).get_constraints()[0].size() == 1);   // the partial push stays, as upstream
+        auto cs2 = ConstraintSystemRef<F>::new_ref();
+        Variable u = cs2.new_witness_variable([&] { return one; });
+        auto M = [u] { return lc<F>() + u; };
+        cs2.enforce_constraint_arity_4(R1CS_PREDICATE_LABEL, M, M, M, M);   // surplus argument dropped silently
+        CHECK(cs2.num_constraints() == 1 && cs2.is_satisfied());
+        cs2.remove_predicate(R1CS_PREDICATE_LABEL);
+        CHECK(!cs2.has_predicate(R1CS_PREDICATE_LABEL) && cs2.num_predicates() == 0 && cs2.num_constraints() == 0);
+        CHECK(!ConstraintSystemRef<F>().has_predicate(R1CS_PREDICATE_LABEL));
+        ConstraintSystemRef<F>().finalize();   // None: no-op
+    }
+    {   // LC (+|-) LC merges, negation, lc_diff (linear_combination.rs:32-38, 300-470)
+        Variable a = Variable::instance(1), b = Variable::witness(0), c = Variable::witness(3);
+        auto l1 = lc_pairs<F>({{two, a}, {one, c}}), l2 = lc_pairs<F>({{one, a}, {two, b}});
+        using T = std::vector<std::pair<F, Variable>>;
+        const F three = two + one, minus_one = F::zero() - one, minus_two = F::zero() - two;
+        CHECK(((l1 + l2).terms == T{{three, a}, {two, b}, {one, c}}));
+        CHECK(((l1 - l2).terms == T{{one, a}, {minus_two, b}, {one, c}}));
+        CHECK(((lc<F>() - l2).terms == T{{minus_one, a}, {minus_two, b}}) && (l1 + lc<F>()).terms == l1.terms);
+        CHECK((lc_diff<F>(a, b).terms == T{{one, a}, {minus_one, b}}) && lc_diff<F>(a, a).terms.empty());
+        CHECK(LinearCombination<F>::from(Variable::Zero()).terms.empty() && LinearCombination<F>::from(F::zero(), a).terms.empty());
+    }
+    {   // Sr1csAdapter (sr1cs/mod.rs:122-264): a*b = c  ->  (a+b)^2 = 4c + s, (a-b)^2 = s; instances re-exposed
+        DummyCircuit<F> c(U(3), U(5), 8, 8);
+        auto cs = ConstraintSystemRef<F>::new_ref();
+        c.generate_constraints(cs);
+        cs.finalize();
+        auto shape = Sr1csAdapter<F>::r1cs_to_sr1cs(cs);
+        // 8 rows -> 16 square constraints + 1 tie for the one public column in use; witnesses: a, b, c copies + 8 squares
+        CHECK(shape.is_in_setup_mode() && shape.num_constraints() == 17 && shape.num_instance_variables() == 2 && shape.num_witness_variables() == 11);
+        CHECK(!shape.has_predicate(R1CS_PREDICATE_LABEL) && shape.has_predicate(SR1CS_PREDICATE_LABEL));
+        auto full = Sr1csAdapter<F>::r1cs_to_sr1cs_with_assignment(cs.inner());
+        CHECK(full.num_constraints() == 17 && full.is_satisfied());
+        CHECK(full->instance_assignment()[1] == U(15));                    // the new instance carries c = a*b
+        auto rows = full.to_matrices().at(SR1CS_PREDICATE_LABEL);
+        std::vector<F> z = full->instance_assignment();
+        z.insert(z.end(), full->witness_assignment().begin(), full->witness_assignment().end());
+        for (size_t i = 0; i < rows[0].size(); i++) {
+            F l = Sr1csAdapter<F>::evaluate_constraint(rows[0][i], z), r = Sr1csAdapter<F>::evaluate_constraint(rows[1][i], z);
+            CHECK(l * l == r);
+        }
+        CHECK(mat_vec_mul(rows[0], z)[0] == U(8));                         // first row: a + b = 3 + 5
+        // a violated R1CS row gives a violated SR1CS system
+        Circuit2<F> bad(one, one, U(3));
+        auto bcs = ConstraintSystemRef<F>::new_ref();
+        bad.generate_constraints(bcs);
+        bcs.finalize();
+        CHECK(!Sr1csAdapter<F>::r1cs_to_sr1cs_with_assignment(bcs.inner()).is_satisfied());
     }
     printf("%s cpu tests: %s\n", name, failures ? "FAILED" : "ok");
 }
