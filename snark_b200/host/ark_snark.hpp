@@ -9,11 +9,13 @@
 #pragma once
 #include <stdexcept>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "../../include/b200snark.h"
 #include "../csrc/curves.cuh"
 #include "ark_relations.hpp"
+#include "ark_std_rng.hpp"
 
 namespace ark_snark {
 
@@ -90,6 +92,24 @@ public:
         pk.delta_g1.assign(k1.begin() + 2 * g1, k1.end());
         b2s_pk_free(ctx_, pkh);
         return pk;
+    }
+
+    // The reference's signatures, `circuit_specific_setup(circuit, &mut rng)` / `prove(&pk, circuit, &mut rng)`
+    // (snark/src/lib.rs:43-54), for any generator with next_u64() (ark_std::test_rng() in tests).  prove draws r then s, as
+    // ark-groth16 does.  setup draws alpha, beta, gamma, delta, tau; upstream additionally draws random G1/G2 generators
+    // between delta and tau, where this backend uses the curve's standard generators -- a valid key, not upstream's bytes.
+    template <class R, class = decltype(std::declval<R&>().next_u64())>
+    ProvingKey<Curve> circuit_specific_setup(ConstraintSynthesizer<F>& circuit, R& rng) {
+        Trapdoor<Curve> td;
+        td.alpha = ark_std::rand<F>(rng); td.beta = ark_std::rand<F>(rng); td.gamma = ark_std::rand<F>(rng); td.delta = ark_std::rand<F>(rng);
+        td.tau = ark_std::rand<F>(rng);
+        return circuit_specific_setup(circuit, static_cast<const Trapdoor<Curve>&>(td));
+    }
+    template <class R, class = decltype(std::declval<R&>().next_u64())>
+    Proof<Curve> prove(const ProvingKey<Curve>& pk, ConstraintSynthesizer<F>& circuit, R& rng) {
+        const F r = ark_std::rand<F>(rng);
+        const F s = ark_std::rand<F>(rng);
+        return prove(pk, circuit, r, s);
     }
 
     // SNARK::prove (snark/src/lib.rs:50-54); r, s are the two field elements upstream draws from rng.

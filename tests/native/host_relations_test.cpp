@@ -1,6 +1,7 @@
 // Tests of the C++ host mirror (snark_b200/host/*.hpp), written after the reference's own unit tests
 // (/root/reference/relations/src/gr1cs/tests/mod.rs, circuit1.rs, circuit2.rs, sr1cs/mod.rs:276-330, variable.rs:206-266).
 //   ./host_relations_test cpu            -> builder tests, no GPU
+//   ./host_relations_test rng            -> ark_std::test_rng() words and Fr::rand draws (compared with oracle/rng.py)
 //   ./host_relations_test gpu <curve> <circuit> tau alpha beta gamma delta r s   -> setup + prove through the C ABI, prints the proof
 #include <cstdio>
 #include <cstdlib>
@@ -323,11 +324,65 @@ static int gpu_prove(const char* circuit, char** a) {
     return 0;
 }
 
+template <class Curve>
+static void rng_draws(const char* tag) {
+    auto rng = ark_std::test_rng();
+    for (int k = 0; k < 20; k++) {
+        auto x = ark_std::rand<typename Curve::Fr>(rng);
+        print_words(tag, std::vector<uint32_t>(x.v, x.v + Curve::Fr::N));
+    }
+}
+
+// SNARK::circuit_specific_setup(circuit, rng) then SNARK::prove(pk, circuit, rng) on one test_rng() stream
+template <class Curve>
+static int gpu_prove_rng(const char* circuit) {
+    using F = typename Curve::Fr;
+    using G = ark_snark::Groth16<Curve>;
+    G g(0);
+    Circuit2<F> c2(F::one(), F::one(), G::from_u64(2));
+    DummyCircuit<F> dc(G::from_u64(3), G::from_u64(5), 16, 16);
+    ConstraintSynthesizer<F>& circ = strcmp(circuit, "circuit2") == 0 ? static_cast<ConstraintSynthesizer<F>&>(c2)
+                                                                        : static_cast<ConstraintSynthesizer<F>&>(dc);
+    auto rng = ark_std::test_rng();
+    auto pk = g.circuit_specific_setup(circ, rng);
+    auto proof = g.prove(pk, circ, rng);
+    print_words("A", proof.a);
+    print_words("B", proof.b);
+    print_words("C", proof.c);
+    print_words("alpha_g1", pk.alpha_g1);
+    return 0;
+}
+
 int main(int argc, char** argv) {
+    if (argc >= 2 && strcmp(argv[1], "rng") == 0) {
+        auto rng = ark_std::test_rng();
+        std::vector<uint32_t> w;
+        for (int i = 0; i < 63; i++) w.push_back(rng.next_u32());
+        const uint64_t straddle = rng.next_u64();          // one word left: low = word 63, high = word 64
+        w.push_back(uint32_t(straddle)); w.push_back(uint32_t(straddle >> 32));
+        for (int i = 0; i < 3; i++) { const uint64_t v = rng.next_u64(); w.push_back(uint32_t(v)); w.push_back(uint32_t(v >> 32)); }
+        print_words("words", w);
+        uint8_t bytes[10];
+        ark_std::test_rng().fill_bytes(bytes, sizeof(bytes));
+        printf("bytes");
+        for (uint8_t b : bytes) printf(" %02x", b);
+        printf("\n");
+        rng_draws<b2s::Bls12_381>("bls12_381");
+        rng_draws<b2s::Bn254>("bn254");
+        return 0;
+    }
     if (argc >= 2 && strcmp(argv[1], "cpu") == 0) {
         cpu_tests<b2s::Bls12_381>("bls12_381");
         cpu_tests<b2s::Bn254>("bn254");
         return failures ? 1 : 0;
+    }
+    if (argc == 4 && strcmp(argv[1], "gpu-rng") == 0) {   // setup + prove with the reference's (circuit, rng) signatures
+        try {
+            return atoi(argv[2]) == 0 ? gpu_prove_rng<b2s::Bls12_381>(argv[3]) : gpu_prove_rng<b2s::Bn254>(argv[3]);
+        } catch (const std::exception& e) {
+            printf("ERROR %s\n", e.what());
+            return 2;
+        }
     }
     if (argc == 11 && strcmp(argv[1], "gpu") == 0) {
         try {
@@ -337,6 +392,6 @@ int main(int argc, char** argv) {
             return 2;
         }
     }
-    printf("usage: %s cpu | gpu <curve 0|1> <circuit2|dummy> tau alpha beta gamma delta r s\n", argv[0]);
+    printf("usage: %s cpu | rng | gpu-rng <curve 0|1> <circuit2|dummy> | gpu <curve 0|1> <circuit2|dummy> tau alpha beta gamma delta r s\n", argv[0]);
     return 64;
 }

@@ -34,6 +34,58 @@ def test_reference_unit_tests_against_cpp_mirror():
     assert "bls12_381 cpu tests: ok" in out.stdout and "bn254 cpu tests: ok" in out.stdout and "FAIL" not in out.stdout
 
 
+def test_cpp_test_rng_matches_oracle_stream():
+    """snark_b200/host/ark_std_rng.hpp against oracle/rng.py (itself pinned to the published ChaCha keystreams): raw words
+    incl. the u64 that straddles a refill, fill_bytes, and 20 Fr::rand draws per curve."""
+    from oracle import rng as orng
+
+    out = subprocess.run([build(), "rng"], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stdout + out.stderr
+    lines = [l.split() for l in out.stdout.splitlines()]
+    ref = orng.test_rng()
+    assert [int(w, 16) for w in lines[0][1:]] == [ref.next_u32() for _ in range(63 + 2 + 6)]
+    assert bytes(int(b, 16) for b in lines[1][1:]) == orng.test_rng().fill_bytes(10)
+    for curve, rows in ((BLS12_381, lines[2:22]), (BN254, lines[22:42])):
+        ref = orng.test_rng()
+        for row in rows:
+            assert row[0] == curve.name
+            got = sum(int(w, 16) << (32 * i) for i, w in enumerate(row[1:]))
+            assert got == orng.field_rand_mont(curve.r, 4, ref)
+
+
+def _parse_words(stdout):
+    import numpy as np
+
+    got = {}
+    for line in stdout.splitlines():
+        tag, *words = line.split()
+        got[tag] = np.array([int(w, 16) for w in words], dtype=np.uint32)
+    return got
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("cid,circuit", [(0, "circuit2"), (1, "dummy")])
+def test_cpp_groth16_with_rng_signatures(cid, circuit):
+    """`circuit_specific_setup(circuit, rng)` + `prove(pk, circuit, rng)` (snark/src/lib.rs:43-54) on one test_rng()
+    stream: alpha, beta, gamma, delta, tau, then r, s -- replayed with oracle/rng.py and checked against the oracle."""
+    from oracle import rng as orng
+
+    curve = [BLS12_381, BN254][cid]
+    out = subprocess.run([build(), "gpu-rng", str(cid), circuit], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stdout + out.stderr
+    got = _parse_words(out.stdout)
+    rng = orng.test_rng()
+    alpha, beta, gamma, delta, tau, rr, ss = (orng.fr_rand(curve, rng) for _ in range(7))
+    cs = orc.circuit2(curve, 1, 1, 2) if circuit == "circuit2" else orc.dummy_circuit(curve, 3, 5, 16, 16)
+    cs.finalize()
+    mats, inst, wit = cs.to_matrices(), cs.instance_assignment, cs.witness_assignment
+    pk = og.setup(curve, mats, len(inst), len(wit), og.Trapdoor(tau, alpha, beta, gamma, delta))
+    A, B, C, h = og.prove(pk, mats, inst, wit, rr, ss)
+    assert og.check_in_exponent(pk, (A, B, C), inst, wit, h, rr, ss)
+    assert unpack_points(curve, 1, got["alpha_g1"])[0] == pk.alpha_g1
+    assert (unpack_points(curve, 1, got["A"])[0], unpack_points(curve, 2, got["B"])[0], unpack_points(curve, 1, got["C"])[0]) == (A, B, C)
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("cid,circuit", [(0, "circuit2"), (0, "dummy"), (1, "circuit2"), (1, "dummy")])
 def test_cpp_groth16_matches_oracle(cid, circuit):
