@@ -57,9 +57,8 @@ def test_setup_matches_oracle_and_proves(be):
         A, B, C, _ = og.prove(pk, mats, inst, wit, rr, ss)
         a, b, c = be.groth16_prove(pkh, m, pack_fr(curve, inst), pack_fr(curve, wit), pack_fr(curve, [rr]), pack_fr(curve, [ss]))
         assert (unpack_points(curve, 1, a)[0], unpack_points(curve, 2, b)[0], unpack_points(curve, 1, c)[0]) == (A, B, C), name
-        if curve is BLS12_381:
-            # SNARK::verify with real pairings on the GPU's own key and proof (no trapdoor involved)
-            assert pairing_verify_packed(curve, vk, len(inst), inst, (a, b, c)), name
+        # SNARK::verify with real pairings on the GPU's own key and proof (no trapdoor involved)
+        assert pairing_verify_packed(curve, vk, len(inst), inst, (a, b, c)), name
         be.pk_free(pkh); be.r1cs_free(m)
 
 

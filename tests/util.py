@@ -131,7 +131,7 @@ def limbs_to_ints(arr, n=8):
 def pairing_verify_packed(curve, vk, n_instance, z_inst, proof_abc):
     """Groth16 verification with real pairings (oracle/pairing.py) on C-ABI arrays: `vk` as returned by
     Backend.groth16_setup (dict of uint32 arrays), z_inst the instance assignment INCLUDING the leading 1 (ints),
-    proof_abc the three uint32 arrays of Backend.groth16_prove.  BLS12-381 only."""
+    proof_abc the three uint32 arrays of Backend.groth16_prove."""
     from oracle import pairing
 
     vk_pts = {
@@ -143,4 +143,4 @@ def pairing_verify_packed(curve, vk, n_instance, z_inst, proof_abc):
     }
     a, b, c = proof_abc
     proof = (unpack_points(curve, 1, a)[0], unpack_points(curve, 2, b)[0], unpack_points(curve, 1, c)[0])
-    return pairing.groth16_verify(vk_pts, list(z_inst[1:]), proof)
+    return pairing.groth16_verify(vk_pts, list(z_inst[1:]), proof, curve)
