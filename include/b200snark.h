@@ -117,6 +117,19 @@ int32_t b2s_g2_sum(b2s_ctx* ctx, const void* xyzz, uint32_t count, void* out_aff
 int32_t b2s_r1cs_upload(b2s_ctx* ctx, uint64_t n_rows, uint64_t n_instance, uint64_t n_witness,
                         const uint64_t* const row_ptr[3], const uint32_t* const col[3],
                         const void* const coeff[3], b2s_r1cs** out);
+/* The same handle built ON THE DEVICE from the constraint system's flat storage, bypassing to_matrices()
+ * (constraint_system.rs:768-804 get_lc + make_row done by kernels):
+ *   args[k]      n_rows Variables: the k-th argument of every R1CS constraint (predicate/mod.rs:81-94 argument_lcs[k]);
+ *                a Variable is the raw u64 of utils/variable.rs:4-14 (tag << 61 | index; Zero 0, One 1, Instance 2,
+ *                Witness 3, SymbolicLc 4)
+ *   lc_offsets   n_lcs + 1 entries, lc_vars / lc_coeffs lc_offsets[n_lcs] entries  (gr1cs/lc_map.rs:51-56)
+ *   pool         the interner's `vec` (gr1cs/field_interner.rs:19-22): pool_len Montgomery field elements,
+ *                pool[0] = ONE, pool[1] = -ONE; lc_coeffs index it
+ * The system must be finalized (no LC may refer to another LC), otherwise B2S_ERR_INVALID_ARG.  HOST pointers. */
+int32_t b2s_r1cs_upload_lcmap(b2s_ctx* ctx, uint64_t n_rows, uint64_t n_instance, uint64_t n_witness,
+                              const uint64_t* const args[3], uint64_t n_lcs, const uint64_t* lc_offsets,
+                              const uint64_t* lc_vars, const uint32_t* lc_coeffs, const void* pool,
+                              uint32_t pool_len, b2s_r1cs** out);
 void b2s_r1cs_free(b2s_ctx* ctx, b2s_r1cs* m);
 /* out_k[i] = <M_k row i, z>, i < n_rows; z has n_instance + n_witness elements.  All buffers share `mem`. */
 int32_t b2s_spmv(b2s_ctx* ctx, const b2s_r1cs* m, const void* z, int32_t mem, void* out_a, void* out_b, void* out_c);

@@ -327,6 +327,26 @@ class ConstraintSystem:
     def is_satisfied(self):
         return self.which_is_unsatisfied() is None
 
+    def to_lcmap(self):
+        """The flat storage `to_matrices()` reads, as the reference holds it: LcMap {offsets, vars, coeffs}
+        (lc_map.rs:51-56), the interner's value vector (field_interner.rs:19-45: [0] = ONE, [1] = -ONE, then values in
+        order of first use, ONE always id 0) and the R1CS predicate's argument_lcs (predicate/mod.rs:81-94).
+        Variables are the raw u64 of variable.rs:4-14 (tag << 61 | index).  Returns a dict of plain lists."""
+        raw = lambda v: (v[0] << 61) | v[1]
+        pool, ids = [1, self.r - 1], {1: 0, self.r - 1: 1}
+        offsets, vars_, coeffs = [0], [], []
+        for row in self.lcs:
+            for c, v in row:
+                c %= self.r
+                if c not in ids:
+                    ids[c] = len(pool)
+                    pool.append(c)
+                coeffs.append(ids[c])
+                vars_.append(raw(v))
+            offsets.append(len(vars_))
+        args = [[raw(cons[k]) for cons in self.constraints] for k in range(3)]
+        return {"offsets": offsets, "vars": vars_, "coeffs": coeffs, "pool": pool, "args": args}
+
     def z(self):
         """instance || witness (sr1cs/mod.rs:199-200)."""
         return self.instance_assignment + self.witness_assignment

@@ -245,6 +245,19 @@ int32_t b2s_r1cs_upload(b2s_ctx* ctx, uint64_t n_rows, uint64_t n_instance, uint
     return r1cs_upload(ctx, n_rows, n_instance, n_witness, row_ptr, col, coeff, out);
 }
 
+int32_t b2s_r1cs_upload_lcmap(b2s_ctx* ctx, uint64_t n_rows, uint64_t n_instance, uint64_t n_witness,
+                              const uint64_t* const args[3], uint64_t n_lcs, const uint64_t* lc_offsets,
+                              const uint64_t* lc_vars, const uint32_t* lc_coeffs, const void* pool, uint32_t pool_len,
+                              b2s_r1cs** out) {
+    LOCK(ctx);
+    if (!out || !args || !lc_offsets || !pool) return fail(ctx, B2S_ERR_INVALID_ARG, "r1cs_upload_lcmap: null argument");
+    for (int k = 0; k < 3; k++)
+        if (!args[k] && n_rows) return fail(ctx, B2S_ERR_INVALID_ARG, "r1cs_upload_lcmap: null argument array %d", k);
+    if (n_lcs && lc_offsets[n_lcs] != 0 && (!lc_vars || !lc_coeffs)) return fail(ctx, B2S_ERR_INVALID_ARG, "r1cs_upload_lcmap: null LC arrays");
+    *out = nullptr;
+    return r1cs_upload_lcmap(ctx, n_rows, n_instance, n_witness, args, n_lcs, lc_offsets, lc_vars, lc_coeffs, pool, pool_len, out);
+}
+
 void b2s_r1cs_free(b2s_ctx* ctx, b2s_r1cs* m) {
     if (!ctx || !m) return;
     std::lock_guard<std::mutex> g(ctx->mu);

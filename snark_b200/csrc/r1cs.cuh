@@ -27,6 +27,10 @@ struct b2s_pk {
 namespace b2s {
 int32_t r1cs_upload(Ctx* c, uint64_t n_rows, uint64_t n_instance, uint64_t n_witness, const uint64_t* const row_ptr[3],
                     const uint32_t* const col[3], const void* const coeff[3], b2s_r1cs** out);
+// lcmap.cu: the same handle from the constraint system's LcMap, CSR built by kernels
+int32_t r1cs_upload_lcmap(Ctx* c, uint64_t n_rows, uint64_t n_instance, uint64_t n_witness, const uint64_t* const args[3],
+                          uint64_t n_lcs, const uint64_t* lc_offsets, const uint64_t* lc_vars, const uint32_t* lc_coeffs,
+                          const void* pool, uint32_t pool_len, b2s_r1cs** out);
 // out_k: device arrays with at least n_rows elements each
 int32_t spmv_run(Ctx* c, const b2s_r1cs* m, const void* z_dev, void* out_a, void* out_b, void* out_c);
 // h_dev: device array of domain elements (output); z_dev: n_instance + n_witness elements

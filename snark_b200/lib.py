@@ -54,6 +54,8 @@ SIGNATURES = {
     "b2s_g2_sum": (c_int32, [c_void_p, c_void_p, c_uint32, c_void_p]),
     "b2s_r1cs_upload": (c_int32, [c_void_p, c_uint64, c_uint64, c_uint64, POINTER(c_void_p), POINTER(c_void_p),
                                   POINTER(c_void_p), POINTER(c_void_p)]),
+    "b2s_r1cs_upload_lcmap": (c_int32, [c_void_p, c_uint64, c_uint64, c_uint64, POINTER(c_void_p), c_uint64, c_void_p, c_void_p,
+                                        c_void_p, c_void_p, c_uint32, POINTER(c_void_p)]),
     "b2s_r1cs_free": (None, [c_void_p, c_void_p]),
     "b2s_spmv": (c_int32, [c_void_p, c_void_p, c_void_p, c_int32, c_void_p, c_void_p, c_void_p]),
     "b2s_witness_map": (c_int32, [c_void_p, c_void_p, c_void_p, c_int32, c_void_p]),
@@ -231,6 +233,16 @@ class Backend:
         co = (c_void_p * 3)(*[m[2].ctypes.data for m in csr])
         h = c_void_p()
         self._ck(self.lib.b2s_r1cs_upload(self.h, n_rows, n_instance, n_witness, rp, col, co, ctypes.byref(h)))
+        return h
+
+    def r1cs_upload_lcmap(self, n_rows, n_instance, n_witness, args, lc_offsets, lc_vars, lc_coeffs, pool):
+        """The same handle, CSR built on the device from the constraint system's LcMap.  args: three uint64[n_rows] arrays
+        of raw Variables; lc_offsets uint64[n_lcs+1]; lc_vars uint64[], lc_coeffs uint32[]; pool uint32[pool_len*8]."""
+        a = (c_void_p * 3)(*[x.ctypes.data for x in args])
+        h = c_void_p()
+        self._ck(self.lib.b2s_r1cs_upload_lcmap(self.h, n_rows, n_instance, n_witness, a, len(lc_offsets) - 1, lc_offsets.ctypes.data,
+                                                lc_vars.ctypes.data, lc_coeffs.ctypes.data, pool.ctypes.data, len(pool) // 8,
+                                                ctypes.byref(h)))
         return h
 
     def r1cs_free(self, m):

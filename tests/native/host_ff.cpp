@@ -106,3 +106,33 @@ extern "C" void ht_generator(int curve, int group, uint32_t* out) {
     if (curve == 1 && group == 1) { auto g = Bn254::g1_generator(); memcpy(out, &g, sizeof(g)); }
     if (curve == 1 && group == 2) { auto g = Bn254::g2_generator(); memcpy(out, &g, sizeof(g)); }
 }
+
+// ---------------------------------------------------------------------------------------------
+// LcMap -> CSR (snark_b200/csrc/lcmap.cuh): the kernels' per-row functions run over all (matrix, row) pairs in
+// the order the GPU grid covers them, with the scan done serially.  Returns the OR of the error bits.
+// Outputs are caller-allocated: row_ptr[k] n_rows + 1 entries; col / coeff_id with room for `cap` entries each.
+#include "../../snark_b200/csrc/lcmap.cuh"
+
+extern "C" uint32_t ht_lcmap_csr(uint64_t n_rows, uint64_t n_instance, uint64_t n_vars, const uint64_t* a0, const uint64_t* a1,
+                                 const uint64_t* a2, uint64_t n_lcs, const uint64_t* lc_offsets, const uint64_t* lc_vars,
+                                 const uint32_t* lc_coeffs, const uint8_t* pool_is_zero, uint32_t pool_len, uint64_t cap,
+                                 uint64_t* rp0, uint64_t* rp1, uint64_t* rp2, uint32_t* col0, uint32_t* col1, uint32_t* col2,
+                                 uint32_t* id0, uint32_t* id1, uint32_t* id2) {
+    b2s::lcmap::View v{lc_offsets, lc_vars, lc_coeffs, pool_is_zero, n_lcs, pool_len, n_instance, n_vars};
+    const uint64_t* args[3] = {a0, a1, a2};
+    uint64_t* rp[3] = {rp0, rp1, rp2};
+    uint32_t* col[3] = {col0, col1, col2};
+    uint32_t* id[3] = {id0, id1, id2};
+    uint32_t err = 0;
+    for (int k = 0; k < 3; k++) {
+        uint64_t at = 0;
+        for (uint64_t r = 0; r < n_rows; r++) {      // count + exclusive scan
+            rp[k][r] = at;
+            at += b2s::lcmap::count_row(v, args[k][r], &err);
+        }
+        rp[k][n_rows] = at;
+        if (at > cap) return err | 0x80000000u;
+        for (uint64_t r = 0; r < n_rows; r++) b2s::lcmap::fill_row(v, args[k][r], col[k] + rp[k][r], id[k] + rp[k][r]);
+    }
+    return err;
+}

@@ -1,0 +1,74 @@
+"""SURVEY 8(f) row 1 on the device: b2s_r1cs_upload_lcmap must give the same handle as b2s_r1cs_upload fed with
+to_matrices() -- same SpMV, same proof.
+
+NOT YET RUN ON A B200: the entry point was written after this round's GPU budget was spent.  Its per-row logic is
+verified on the host (tests/test_host_lcmap.py runs the kernels' own functions), the kernels cross-compile, but the
+device path itself is unconfirmed, so this file is opt-in (B2S_RUN_UNVALIDATED=1) until it has been seen green."""
+import os
+import random
+
+import numpy as np
+import pytest
+
+from oracle import groth16 as og
+from oracle import r1cs as orc
+from oracle.params import BLS12_381, BN254
+from tests.test_host_lcmap import circuits
+from tests.util import csr_from_rows, pack_fr, unpack_fr, unpack_points
+
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.skipif(os.environ.get("B2S_RUN_UNVALIDATED") != "1", reason="device LcMap ingest not yet validated on a B200")]
+CURVES = [BLS12_381, BN254]
+
+
+@pytest.fixture(scope="module", params=[0, 1], ids=["bls12_381", "bn254"])
+def be(request):
+    from snark_b200 import Backend
+
+    b = Backend(curve=request.param)
+    yield b
+    b.close()
+
+
+def upload_lcmap(be, curve, cs):
+    lm = cs.to_lcmap()
+    args = [np.array(a, dtype=np.uint64) for a in lm["args"]]
+    return be.r1cs_upload_lcmap(len(args[0]), cs.num_instance_variables, cs.num_witness_variables, args,
+                                np.array(lm["offsets"], dtype=np.uint64), np.array(lm["vars"] or [0], dtype=np.uint64),
+                                np.array(lm["coeffs"] or [0], dtype=np.uint32), pack_fr(curve, lm["pool"]))
+
+
+def test_lcmap_handle_equals_matrix_handle(be):
+    curve = CURVES[be.curve]
+    rng = random.Random(0xB2000005)
+    for name, cs in circuits(curve).items():
+        mats, inst, wit = cs.to_matrices(), cs.instance_assignment, cs.witness_assignment
+        n_rows = len(mats[0])
+        m_ref = be.r1cs_upload(n_rows, len(inst), len(wit), [csr_from_rows(curve, M) for M in mats])
+        m_lc = upload_lcmap(be, curve, cs)
+        assert be.domain_size(m_lc) == be.domain_size(m_ref), name
+        z = pack_fr(curve, inst + wit)
+        ref, got = be.spmv(m_ref, z, n_rows), be.spmv(m_lc, z, n_rows)
+        for k in range(3):
+            assert np.array_equal(ref[k], got[k]), (name, k)
+            assert unpack_fr(curve, got[k]) == orc.mat_vec_mul(curve.r, mats[k], inst + wit), (name, k)
+        if cs.is_satisfied():
+            td = og.Trapdoor(*[rng.randrange(1, curve.r) for _ in range(5)])
+            pkh, _ = be.groth16_setup(m_lc, pack_fr(curve, [td.tau, td.alpha, td.beta, td.gamma, td.delta]), len(inst))
+            pk = og.setup(curve, mats, len(inst), len(wit), td)
+            rr, ss = rng.randrange(curve.r), rng.randrange(curve.r)
+            A, B, C, _ = og.prove(pk, mats, inst, wit, rr, ss)
+            a, b, c = be.groth16_prove(pkh, m_lc, pack_fr(curve, inst), pack_fr(curve, wit), pack_fr(curve, [rr]), pack_fr(curve, [ss]))
+            assert (unpack_points(curve, 1, a)[0], unpack_points(curve, 2, b)[0], unpack_points(curve, 1, c)[0]) == (A, B, C), name
+            be.pk_free(pkh)
+        be.r1cs_free(m_ref); be.r1cs_free(m_lc)
+
+
+def test_lcmap_errors(be):
+    from snark_b200.lib import B2SError
+
+    curve = CURVES[be.curve]
+    cs = orc.circuit2(curve, 1, 1, 2)          # not finalized
+    with pytest.raises(B2SError) as e:
+        upload_lcmap(be, curve, cs)
+    assert e.value.code == 16 and "finalize" in str(e.value)
