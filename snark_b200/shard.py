@@ -35,6 +35,29 @@ def shard_plan(n_instance, n_witness, domain_size, rank, world):
     return plan
 
 
+def plan_window_units(world, nwin_g1, nwin_g2, g2_cost=3.16, n_g1_msms=4):
+    """Alternative partition for round 2 (not wired to kernels yet): instead of cutting every MSM by base range --
+    which leaves each rank a smaller Pippenger problem (more windows, batched-affine rounds off) -- hand out whole
+    (MSM, window) units over the FULL base range; every rank then works at the single-GPU operating point and only the
+    replicated key (9 GiB at 2^24) is the price.  Longest-processing-time greedy; a G2 window costs `g2_cost` G1
+    windows (357 ms vs 113 ms per 2^24-point MSM).
+    Returns (units per rank: list of (group, msm index, window), load per rank, balance = mean load / max load)."""
+    import heapq
+
+    units = [(1.0, (1, m, w)) for m in range(n_g1_msms) for w in range(nwin_g1)] + [(float(g2_cost), (2, 0, w)) for w in range(nwin_g2)]
+    heap = [(0.0, r) for r in range(world)]
+    heapq.heapify(heap)
+    owned = [[] for _ in range(world)]
+    for cost, unit in sorted(units, key=lambda cu: (-cu[0], cu[1])):
+        load, r = heapq.heappop(heap)
+        owned[r].append(unit)
+        heapq.heappush(heap, (load + cost, r))
+    loads = [0.0] * world
+    for load, r in heap:
+        loads[r] = load
+    return owned, loads, (sum(loads) / world) / max(loads)
+
+
 def pack_partials(g1_partials, g2_partial):
     """One rank's contribution to the all-gather: 4 G1 XYZZ + 1 G2 XYZZ as one flat uint32 vector."""
     return np.concatenate([np.asarray(g1_partials, dtype=np.uint32).reshape(-1), np.asarray(g2_partial, dtype=np.uint32).reshape(-1)])

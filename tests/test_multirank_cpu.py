@@ -83,6 +83,17 @@ def _worker(rank, world, port, q):
         dist.destroy_process_group()
 
 
+def test_window_unit_plan_balances():
+    """Round-2 partition by (MSM, window) units: every unit owned exactly once, >= 95 % balance up to 8 ranks."""
+    for world in (1, 2, 4, 8):
+        owned, loads, balance = shard.plan_window_units(world, 13, 13)
+        flat = [u for lst in owned for u in lst]
+        assert len(flat) == len(set(flat)) == 4 * 13 + 13
+        assert {u for u in flat if u[0] == 2} == {(2, 0, w) for w in range(13)}
+        assert balance >= 0.95 and abs(sum(loads) - (52 + 13 * 3.16)) < 1e-9
+    assert shard.plan_window_units(8, 16, 16)[2] >= 0.93
+
+
 def test_two_rank_gloo_shard_and_join():
     with socket.socket() as sk:
         sk.bind(("127.0.0.1", 0))
