@@ -2,7 +2,7 @@
 //! SOURCE ONLY -- never compiled here (no Rust toolchain in the build image).  See INTEGRATION.md.
 use std::os::raw::c_void;
 
-use ark_ec::pairing::Pairing;
+use ark_ec::{pairing::Pairing, AffineRepr};
 use ark_groth16::{Groth16, PreparedVerifyingKey, Proof, ProvingKey, VerifyingKey};
 use ark_relations::gr1cs::{
     ConstraintSynthesizer, ConstraintSystem, Matrix, OptimizationGoal, SynthesisError, R1CS_PREDICATE_LABEL,
@@ -75,20 +75,83 @@ pub fn to_csr<F: Copy>(m: &Matrix<F>) -> (Vec<u64>, Vec<u32>, Vec<F>) {
     (rp, col, co)
 }
 
+/// The in-memory bytes of a field element.  ark-ff's `Fp<MontBackend<_, N>>` is `BigInt<N>` (N little-endian u64
+/// limbs, Montgomery form) plus a zero-sized marker, and `Fp2` is `{ c0, c1 }` of those -- exactly the C-ABI layout.
+fn raw<T>(t: &T) -> &[u8] { unsafe { core::slice::from_raw_parts((t as *const T).cast::<u8>(), core::mem::size_of::<T>()) } }
+
+/// `Affine {{ x, y, infinity }}` -> x || y, all-zero bytes for the point at infinity (include/b200snark.h, "Layouts").
+pub fn pack_points<G: AffineRepr>(pts: &[G]) -> Vec<u8> {
+    let w = core::mem::size_of::<G::BaseField>();
+    let mut out = vec![0u8; 2 * w * pts.len()];
+    for (i, p) in pts.iter().enumerate() {
+        if let Some((x, y)) = p.xy() {
+            out[2 * w * i..2 * w * i + w].copy_from_slice(raw(&x));
+            out[2 * w * i + w..2 * w * (i + 1)].copy_from_slice(raw(&y));
+        }
+    }
+    out
+}
+
+/// x || y (Montgomery limbs; zeros = infinity) -> `Affine`.  The coordinates come from the prover, so they are on the
+/// curve by construction: `new_unchecked`.
+pub fn unpack_point<G: AffineRepr>(bytes: &[u8]) -> G where G::BaseField: Copy {
+    let w = core::mem::size_of::<G::BaseField>();
+    if bytes.iter().all(|b| *b == 0) { return G::zero(); }
+    let read = |b: &[u8]| -> G::BaseField { unsafe { core::ptr::read_unaligned(b.as_ptr().cast::<G::BaseField>()) } };
+    G::new_unchecked(read(&bytes[..w]), read(&bytes[w..2 * w]))
+}
+
+fn check(ctx: *mut B2sCtx, st: i32) -> Result<(), B200Error> {
+    let _ = ctx;   // b2s_last_error(ctx) carries the message for logs
+    if st == 0 { Ok(()) } else { Err(B200Error::from_status(st)) }
+}
+
 pub struct Groth16B200<E: Pairing>(core::marker::PhantomData<E>);
 
 /// Device handles for one (proving key, circuit shape): matrices and key are witness independent.
 pub struct Resident { pub ctx: *mut B2sCtx, pub pk: *mut B2sPk, pub mat: *mut B2sR1cs }
 
 impl<E: Pairing> Groth16B200<E> {
-    /// Upload the matrices and the key (packing `Affine { x, y, infinity }` into x||y, zeros for infinity).
-    pub fn make_resident(_pk: &ProvingKey<E>, _mats: &[Matrix<E::ScalarField>], _n_inst: usize, _n_wit: usize)
+    /// Upload the matrices and the key once per (key, circuit shape).  `curve_id`: 0 = BLS12-381, 1 = BN254.
+    pub fn make_resident(curve_id: i32, pk: &ProvingKey<E>, mats: &[Matrix<E::ScalarField>], n_inst: usize, n_wit: usize)
         -> Result<Resident, B200Error> {
-        unimplemented!("pack points field-wise, call b2s_r1cs_upload / b2s_pk_upload; see INTEGRATION.md section 2")
+        let mut ctx: *mut B2sCtx = core::ptr::null_mut();
+        check(ctx, unsafe { b2s_ctx_create(curve_id, 0, &mut ctx) })?;
+        let csr: Vec<_> = mats.iter().map(to_csr).collect();
+        let rp: Vec<*const u64> = csr.iter().map(|m| m.0.as_ptr()).collect();
+        let col: Vec<*const u32> = csr.iter().map(|m| m.1.as_ptr()).collect();
+        let co: Vec<*const c_void> = csr.iter().map(|m| m.2.as_ptr().cast()).collect();
+        let mut mat: *mut B2sR1cs = core::ptr::null_mut();
+        check(ctx, unsafe { b2s_r1cs_upload(ctx, mats[0].len() as u64, n_inst as u64, n_wit as u64, rp.as_ptr(), col.as_ptr(), co.as_ptr(), &mut mat) })?;
+        let n = (mats[0].len() + n_inst).next_power_of_two() as u64;          // the QAP domain (LibsnarkReduction)
+        let (alpha, beta1, delta1) = (pack_points(&[pk.vk.alpha_g1]), pack_points(&[pk.beta_g1]), pack_points(&[pk.delta_g1]));
+        let (beta2, delta2) = (pack_points(&[pk.vk.beta_g2]), pack_points(&[pk.vk.delta_g2]));
+        let (a, b1, b2, h, l) = (pack_points(&pk.a_query), pack_points(&pk.b_g1_query), pack_points(&pk.b_g2_query),
+                                 pack_points(&pk.h_query), pack_points(&pk.l_query));
+        let d = B2sPkDesc {
+            n_instance: n_inst as u64, n_witness: n_wit as u64, domain_size: n,
+            alpha_g1: alpha.as_ptr().cast(), beta_g1: beta1.as_ptr().cast(), delta_g1: delta1.as_ptr().cast(),
+            beta_g2: beta2.as_ptr().cast(), delta_g2: delta2.as_ptr().cast(),
+            a_query: a.as_ptr().cast(), a_off: 0, a_len: pk.a_query.len() as u64,
+            b_g1_query: b1.as_ptr().cast(), b1_off: 0, b1_len: pk.b_g1_query.len() as u64,
+            b_g2_query: b2.as_ptr().cast(), b2_off: 0, b2_len: pk.b_g2_query.len() as u64,
+            h_query: h.as_ptr().cast(), h_off: 0, h_len: pk.h_query.len() as u64,
+            l_query: l.as_ptr().cast(), l_off: 0, l_len: pk.l_query.len() as u64,
+        };
+        let mut pkh: *mut B2sPk = core::ptr::null_mut();
+        check(ctx, unsafe { b2s_pk_upload(ctx, &d, 0 /* B2S_MEM_HOST */, &mut pkh) })?;
+        Ok(Resident { ctx, pk: pkh, mat })
     }
 }
 
-impl<E: Pairing> SNARK<E::ScalarField> for Groth16B200<E> {
+impl Drop for Resident {
+    fn drop(&mut self) { unsafe { b2s_pk_free(self.ctx, self.pk); b2s_r1cs_free(self.ctx, self.mat); b2s_ctx_destroy(self.ctx); } }
+}
+
+/// Which curve id the backend should use for `E` (the backend supports the two curves of the north-star).
+pub trait B200Curve { const CURVE_ID: i32; }
+
+impl<E: Pairing + B200Curve> SNARK<E::ScalarField> for Groth16B200<E> {
     type ProvingKey = ProvingKey<E>;
     type VerifyingKey = VerifyingKey<E>;
     type Proof = Proof<E>;
@@ -112,15 +175,15 @@ impl<E: Pairing> SNARK<E::ScalarField> for Groth16B200<E> {
         cs.finalize();
         let mats = cs.to_matrices()?.remove(R1CS_PREDICATE_LABEL).ok_or(SynthesisError::MissingCS)?;
         let (zi, zw) = (cs.instance_assignment()?, cs.witness_assignment()?);
-        let h = Self::make_resident(pk, &mats, zi.len(), zw.len())?;   // cached per circuit in a real adapter
-        let g1 = 2 * core::mem::size_of::<E::BaseField>();
+        let h = Self::make_resident(E::CURVE_ID, pk, &mats, zi.len(), zw.len())?;   // cache per (key, circuit) in a long-lived prover
+        let g1 = 2 * core::mem::size_of::<<E::G1Affine as AffineRepr>::BaseField>();
         let (mut a, mut b, mut c) = (vec![0u8; g1], vec![0u8; 2 * g1], vec![0u8; g1]);
         let st = unsafe {
             b2s_groth16_prove(h.ctx, h.pk, h.mat, zi.as_ptr().cast(), zw.as_ptr().cast(), (&r as *const E::ScalarField).cast(),
                               (&s as *const E::ScalarField).cast(), a.as_mut_ptr().cast(), b.as_mut_ptr().cast(), c.as_mut_ptr().cast())
         };
         if st != 0 { return Err(B200Error::from_status(st)); }
-        unimplemented!("unpack a, b, c (x||y Montgomery limbs, zeros = infinity) into Proof {{ a, b, c }}")
+        Ok(Proof { a: unpack_point::<E::G1Affine>(&a), b: unpack_point::<E::G2Affine>(&b), c: unpack_point::<E::G1Affine>(&c) })
     }
 
     fn process_vk(vk: &Self::VerifyingKey) -> Result<Self::ProcessedVerifyingKey, Self::Error> {
@@ -134,4 +197,7 @@ impl<E: Pairing> SNARK<E::ScalarField> for Groth16B200<E> {
     }
 }
 
-impl<E: Pairing> CircuitSpecificSetupSNARK<E::ScalarField> for Groth16B200<E> {}
+impl<E: Pairing + B200Curve> CircuitSpecificSetupSNARK<E::ScalarField> for Groth16B200<E> {}
+
+// e.g. in the application:  impl B200Curve for ark_bls12_381::Bls12_381 { const CURVE_ID: i32 = 0; }
+//                           impl B200Curve for ark_bn254::Bn254 { const CURVE_ID: i32 = 1; }
