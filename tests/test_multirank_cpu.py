@@ -7,6 +7,7 @@ import socket
 
 import numpy as np
 import pytest
+import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
@@ -106,4 +107,142 @@ def test_two_rank_gloo_shard_and_join():
     for p in procs:
         p.join(180)
         assert p.exitcode == 0
+    assert q.get(timeout=5) is True
+
+
+# ---- distributed four-step NTT (snark_b200/dist_ntt.py), oracle arithmetic as the stand-in engine ---------------------
+class _OracleNttEngine:
+    """Python big-int stand-in for the GPU kernels: tiles are object arrays of ints (limbs axis of length 1)."""
+
+    def __init__(self, curve):
+        from oracle import ntt as ontt
+
+        self.curve, self.ontt = curve, ontt
+
+    def _w(self, N, inverse):
+        w = self.curve.omega(N.bit_length() - 1)
+        return pow(w, -1, self.curve.r) if inverse else w
+
+    def _raw(self, vec, inverse):
+        """size-n transform without the 1/n of the inverse (the plan applies 1/N once at the end)."""
+        out = self.ontt.ntt(self.curve, [int(v) for v in vec], inverse=inverse)
+        return [o * len(vec) % self.curve.r for o in out] if inverse else out
+
+    def ntt_axis0(self, a, inverse):
+        out = a.copy()
+        for j in range(a.shape[1]):
+            out[:, j, 0] = self._raw(list(a[:, j, 0]), inverse)
+        return out
+
+    def ntt_axis1(self, a, inverse):
+        out = a.copy()
+        for i in range(a.shape[0]):
+            out[i, :, 0] = self._raw(list(a[i, :, 0]), inverse)
+        return out
+
+    def mul_pow(self, a, row0, col0, inverse, N):
+        w, r = self._w(N, inverse), self.curve.r
+        out = a.copy()
+        for i in range(a.shape[0]):
+            for j in range(a.shape[1]):
+                out[i, j, 0] = int(a[i, j, 0]) * pow(w, (row0 + i) * (col0 + j), r) % r
+        return out
+
+    def mul_geometric(self, a, idx, use_g_inv, scale_n_inv, N):
+        r, g = self.curve.r, self.curve.fr_generator
+        out = a.copy()
+        n_inv = pow(N, -1, r) if scale_n_inv else 1
+        for i in range(a.shape[0]):
+            for j in range(a.shape[1]):
+                k = int(idx[i, j])
+                f = n_inv
+                if scale_n_inv and use_g_inv:
+                    f = f * pow(g, -k, r) % r
+                elif not scale_n_inv:
+                    f = pow(g, k, r)
+                out[i, j, 0] = int(a[i, j, 0]) * f % r
+        return out
+
+
+def _ntt_worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from oracle import ntt as ontt
+        from oracle.params import BN254 as curve
+        from snark_b200 import dist_ntt
+
+        class _IntTiles(dist_ntt.FourStepNtt):
+            pass
+
+        # ints do not fit the uint32 wire format of all_to_all_tiles: ship them as 8 limbs and rebuild
+        def to_limbs(t):
+            flat = np.zeros(t.shape[:2] + (8,), dtype=np.uint32)
+            for i in range(t.shape[0]):
+                for j in range(t.shape[1]):
+                    v = int(t[i, j, 0])
+                    flat[i, j] = [(v >> (32 * k)) & 0xFFFFFFFF for k in range(8)]
+            return flat
+
+        def from_limbs(f):
+            out = np.empty(f.shape[:2] + (1,), dtype=object)
+            for i in range(f.shape[0]):
+                for j in range(f.shape[1]):
+                    out[i, j, 0] = sum(int(f[i, j, k]) << (32 * k) for k in range(8))
+            return out
+
+        orig = dist_ntt.all_to_all_tiles
+        dist_ntt.all_to_all_tiles = lambda d, tiles, w: [from_limbs(x) for x in orig(d, [to_limbs(t) for t in tiles], w)]
+        ok = True
+        rng = random.Random(99)
+        for log_n in (4, 6):
+            N = 1 << log_n
+            x = [rng.randrange(curve.r) for _ in range(N)]              # same data on every rank
+            plan = dist_ntt.FourStepNtt(dist, rank, world, log_n, _OracleNttEngine(curve))
+            idx_in = dist_ntt.owned_indices_in(plan.N1, plan.N2, rank, world)
+            idx_out = dist_ntt.owned_indices_out(plan.N1, plan.N2, rank, world)
+            tile = np.empty(idx_in.shape + (1,), dtype=object)
+            for i in range(idx_in.shape[0]):
+                for j in range(idx_in.shape[1]):
+                    tile[i, j, 0] = x[int(idx_in[i, j])]
+
+            def check(z, full):
+                return all(int(z[i, j, 0]) == full[int(idx_out[i, j])] for i in range(z.shape[0]) for j in range(z.shape[1]))
+
+            fwd = plan.transform(tile)
+            ok &= check(fwd, ontt.ntt(curve, x))
+            ok &= check(plan.transform(tile, inverse=True), ontt.ntt(curve, x, inverse=True))
+            ok &= check(plan.transform(tile, coset=True), ontt.coset_ntt(curve, x))
+            ok &= check(plan.transform(tile, inverse=True, coset=True), ontt.coset_intt(curve, x))
+            # chained without re-gathering: forward then inverse gives x back, in the layout the chain ends in
+            back = plan.transform(plan.out_as_in(fwd), inverse=True)
+            ok &= check(back, x)
+            # the two layouts partition the index space
+            both = [torch.zeros(N, dtype=torch.int64) for _ in range(2)]
+            both[0][torch.from_numpy(idx_in.reshape(-1))] = 1
+            both[1][torch.from_numpy(idx_out.reshape(-1))] = 1
+            for t in both:
+                dist.all_reduce(t)
+                ok &= bool((t == 1).all())
+        if rank == 0:
+            q.put(ok)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_gloo_four_step_ntt():
+    """One all-to-all per transform; forward / inverse / coset forms equal the oracle's full-size transforms on the
+    indices each rank ends up owning; transforms chain without re-gathering (N1 == N2)."""
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_ntt_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(180)
+    assert all(p.exitcode == 0 for p in procs)
     assert q.get(timeout=5) is True
