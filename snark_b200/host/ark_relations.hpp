@@ -16,6 +16,8 @@
 //   ConstraintSystemRef               relations/src/gr1cs/constraint_system_ref.rs:26-34,235-250,345-383
 //   ConstraintSynthesizer             relations/src/gr1cs/mod.rs:54-61
 //   Matrix, mat_vec_mul, transpose    relations/src/utils/matrix.rs:4-36
+//   FieldInterner, InternedField      relations/src/gr1cs/field_interner.rs:13-69
+//   LcMap                             relations/src/gr1cs/lc_map.rs:51-56,87-215 (the flat storage b2s_r1cs_upload_lcmap ingests)
 //   PolynomialPredicate               relations/src/gr1cs/predicate/polynomial_constraint.rs:16-73
 //   PredicateConstraintSystem         relations/src/gr1cs/predicate/mod.rs:81-217
 //   InstanceOutliner, outline_*       relations/src/gr1cs/instance_outliner.rs:17-80; constraint_system.rs:807-863
@@ -35,6 +37,7 @@
 #include <optional>
 #include <stdexcept>
 #include <string>
+#include <unordered_map>
 #include <utility>
 #include <vector>
 
@@ -229,6 +232,77 @@ using Label = std::string;
 inline const Label R1CS_PREDICATE_LABEL = "R1CS";     // polynomial_constraint.rs:68-69
 inline const Label SR1CS_PREDICATE_LABEL = "SR1CS";   // polynomial_constraint.rs:71-73
 
+// field_interner.rs:13-69.  One pool entry per DISTINCT coefficient: vec[0] = ONE, vec[1] = -ONE, ids index vec; ONE is
+// always id 0 (which is also what the SpMV kernel keys its "skip the multiplication" on).  Values are compared by their
+// in-memory bytes (canonical Montgomery form, so equal elements have equal bytes).
+struct InternedField {
+    uint32_t id;
+    bool operator==(const InternedField& o) const { return id == o.id; }
+};
+template <class F>
+class FieldInterner {
+public:
+    FieldInterner() { intern(F::one()); intern(F::zero() - F::one()); }
+    InternedField get_or_intern(const F& value) {
+        if (value == F::one()) return {0};
+        auto it = map_.find(key(value));
+        return it != map_.end() ? InternedField{it->second} : intern(value);
+    }
+    std::optional<F> value(InternedField id) const { return id.id < vec_.size() ? std::optional<F>(vec_[id.id]) : std::nullopt; }
+    const std::vector<F>& vec() const { return vec_; }   // the pool, in the layout b2s_r1cs_upload_lcmap takes
+private:
+    static std::string key(const F& v) { return std::string(reinterpret_cast<const char*>(&v), sizeof(F)); }
+    InternedField intern(const F& v) {
+        const uint32_t id = uint32_t(vec_.size());
+        map_[key(v)] = id;
+        vec_.push_back(v);
+        return {id};
+    }
+    std::unordered_map<std::string, uint32_t> map_;
+    std::vector<F> vec_;
+};
+
+// lc_map.rs:51-215.  All linear combinations in three flat arrays: LC i is vars[offsets[i] .. offsets[i+1]) with the
+// interned coefficients at the same positions.
+template <class F>
+class LcMap {
+public:
+    using Term = std::pair<F, Variable>;
+    void push(const std::vector<Term>& lc, FieldInterner<F>& interner) {
+        for (const auto& t : lc) { coeffs_.push_back(interner.get_or_intern(t.first)); vars_.push_back(t.second); }
+        offsets_.push_back(uint64_t(vars_.size()));
+    }
+    size_t num_lcs() const { return offsets_.size() - 1; }
+    size_t total_lc_size() const { return vars_.size(); }
+    // (coefficient id, variable) pairs of LC `idx`, or nullopt past the end (lc_map.rs:188-204)
+    std::optional<std::vector<std::pair<InternedField, Variable>>> get(size_t idx) const {
+        if (idx >= num_lcs()) return std::nullopt;
+        std::vector<std::pair<InternedField, Variable>> out;
+        for (uint64_t e = offsets_[idx]; e < offsets_[idx + 1]; e++) out.emplace_back(coeffs_[e], vars_[e]);
+        return out;
+    }
+    // to_non_interned_lc (lc_map.rs:58-63)
+    std::vector<Term> get_lc(size_t idx, const FieldInterner<F>& interner) const {
+        std::vector<Term> out;
+        for (uint64_t e = offsets_.at(idx); e < offsets_.at(idx + 1); e++) out.emplace_back(*interner.value(coeffs_[e]), vars_[e]);
+        return out;
+    }
+    // iter(): f(lc index, first term, one-past-last term) over every LC
+    template <class Fn> void for_each_lc(Fn&& f) const { for (size_t i = 0; i < num_lcs(); i++) f(i, offsets_[i], offsets_[i + 1]); }
+    // lc_vars_iter_mut(): f gets each LC's variables as a mutable [begin, end) range
+    template <class Fn> void lc_vars_iter_mut(Fn&& f) {
+        for (size_t i = 0; i < num_lcs(); i++) f(vars_.data() + offsets_[i], vars_.data() + offsets_[i + 1]);
+    }
+    const std::vector<Variable>& vars() const { return vars_; }
+    const std::vector<InternedField>& coeffs() const { return coeffs_; }
+    const std::vector<uint64_t>& offsets() const { return offsets_; }
+private:
+    std::vector<Variable> vars_;
+    std::vector<InternedField> coeffs_;
+    std::vector<uint64_t> offsets_{0};
+};
+static_assert(sizeof(InternedField) == 4, "coefficient ids are 4 bytes (lc_map.rs: 4 B/nnz)");
+
 template <class F> class ConstraintSystem;
 
 // A sparse multivariate polynomial; the predicate holds iff it evaluates to zero (polynomial_constraint.rs:16-66).
@@ -324,7 +398,7 @@ public:
 
     ConstraintSystem() {   // constraint_system.rs:109-139: One is instance 0, LC 0 is the empty LC, R1CS is registered
         instance_assignment_.push_back(F::one());
-        lcs_.push_back({});
+        lc_map_.push({}, interner_);
         lc_assignment_.push_back(F::zero());
         register_predicate(R1CS_PREDICATE_LABEL, PredicateConstraintSystem<F>::new_r1cs());
     }
@@ -441,15 +515,14 @@ public:
     void inline_all_lcs() {   // :717-758
         if (!should_construct_matrices()) return;
         bool any_used = false;
-        for (const auto& l : lcs_) for (const auto& t : l) any_used |= t.second.is_lc();
+        for (const Variable& v : lc_map_.vars()) any_used |= v.is_lc();
         if (!any_used) return;   // early return leaves LCs untouched (:722-725)
-        std::vector<std::vector<std::pair<F, Variable>>> inlined;
-        inlined.reserve(lcs_.size());
+        LcMap<F> inlined;
         LC out;
-        for (const auto& l : lcs_) {
-            for (const auto& [coeff, var] : l) {
+        for (size_t i = 0; i < lc_map_.num_lcs(); i++) {
+            for (const auto& [coeff, var] : lc_map_.get_lc(i, interner_)) {
                 if (auto li = var.get_lc_index()) {
-                    const auto& sub = inlined[*li];   // already transformed: guaranteed by ordering
+                    const auto sub = inlined.get_lc(*li, interner_);   // already transformed: guaranteed by ordering
                     if (coeff == F::one()) out.terms.insert(out.terms.end(), sub.begin(), sub.end());
                     else for (const auto& [c, v] : sub) if (!v.is_zero() && !c.is_zero()) out.terms.emplace_back(coeff * c, v);
                 } else {
@@ -457,10 +530,10 @@ public:
                 }
             }
             out.compactify();
-            inlined.push_back(out.terms);
+            inlined.push(out.terms, interner_);
             out.terms.clear();
         }
-        lcs_ = std::move(inlined);
+        lc_map_ = std::move(inlined);
     }
 
     // -- instance outlining (constraint_system.rs:807-863)
@@ -477,18 +550,19 @@ public:
                 return inst[i];
             }));
         // rewritten in place: the terms keep their positions, so rows may come out unsorted (the C ABI allows that)
-        for (auto& l : lcs_)
-            for (auto& t : l) {
-                if (t.second.is_instance()) t.second = instance_to_witness[t.second.payload()];
-                else if (t.second.is_one()) t.second = one_witness;
+        lc_map_.lc_vars_iter_mut([&](Variable* v, Variable* end) {
+            for (; v != end; ++v) {
+                if (v->is_instance()) *v = instance_to_witness[v->payload()];
+                else if (v->is_one()) *v = one_witness;
             }
+        });
         outliner.func(*this, instance_to_witness);
     }
 
     // -- export (constraint_system.rs:768-804): label -> one matrix per predicate argument
     LC get_lc(Variable v) const {
         if (v.is_zero()) return {};
-        if (v.is_lc()) return LC(lcs_.at(v.payload()));
+        if (v.is_lc()) return LC(lc_map_.get_lc(v.payload(), interner_));
         return LC({{F::one(), v}});
     }
     std::vector<std::pair<F, size_t>> make_row(const LC& l) const {
@@ -504,6 +578,10 @@ public:
         for (const auto& kv : predicates_) m[kv.first] = kv.second.to_matrices(*this);
         return m;
     }
+
+    // -- flat storage, as b2s_r1cs_upload_lcmap takes it (include/b200snark.h)
+    const LcMap<F>& lc_map() const { return lc_map_; }
+    const FieldInterner<F>& field_interner() const { return interner_; }
 
     // -- satisfaction (constraint_system.rs:652-687): "<label> - <index>" of the first failing constraint, predicates
     // visited in label order (the form upstream reports when no ConstraintLayer trace is installed)
@@ -523,7 +601,7 @@ private:
         if (t.empty() || (t.size() == 1 && t[0].second.is_zero())) return Variable::symbolic_lc(0);
         if (t.size() == 1 && t[0].first == F::one()) return t[0].second;
         size_t idx = num_lcs_++;
-        lcs_.push_back(t);
+        lc_map_.push(t, interner_);
         if (should_generate_lc_assignments()) {   // assignment.rs:40-52
             F acc = F::zero();
             for (const auto& [c, v] : t) acc = acc + c * *assigned_value(v);
@@ -534,7 +612,8 @@ private:
 
     size_t num_instance_ = 1, num_witness_ = 0, num_lcs_ = 1;
     std::vector<F> instance_assignment_, witness_assignment_, lc_assignment_;
-    std::vector<std::vector<std::pair<F, Variable>>> lcs_;
+    LcMap<F> lc_map_;              // `pub lc_map` upstream (#[doc(hidden)], constraint_system.rs:85-86)
+    FieldInterner<F> interner_;    // private upstream (constraint_system.rs:88)
     std::map<Label, PredicateConstraintSystem<F>> predicates_;   // BTreeMap upstream: iteration in label order
     std::optional<InstanceOutliner<F>> instance_outliner_;
     SynthesisMode mode_ = SynthesisMode::Prove(true, true);   // constraint_system.rs:128-131

@@ -7,6 +7,7 @@
 // (include/b200snark.h) for everything else: b2s_groth16_setup builds the key, b2s_groth16_prove the proof.
 // No setup or prover arithmetic runs on the CPU.
 #pragma once
+#include <cstdlib>
 #include <stdexcept>
 #include <string>
 #include <utility>
@@ -149,6 +150,10 @@ private:
     // Matrix<F> (to_matrices(), constraint_system.rs:768-774) -> CSR -> device (once per circuit in a long-lived
     // prover; per call in this thin mirror)
     b2s_r1cs* upload_matrices(const ConstraintSystemRef<F>& cs) {
+        // B2S_HOST_LCMAP=1: hand the flat LcMap to the device and let kernels build the CSR (b2s_r1cs_upload_lcmap),
+        // skipping to_matrices().  Opt-in until the device path has been run on a B200 (DESIGN.md section 0, row f).
+        const char* lc = std::getenv("B2S_HOST_LCMAP");
+        if (lc && lc[0] == '1') return upload_lcmap(cs);
         const auto all = cs.to_matrices();   // BTreeMap<Label, Vec<Matrix>> upstream; Groth16 takes the R1CS entry
         const auto it = all.find(ark_relations::gr1cs::R1CS_PREDICATE_LABEL);
         if (it == all.end() || it->second.size() != 3) throw BackendError(B2S_ERR_INVALID_ARG, "constraint system has no R1CS predicate");
@@ -168,6 +173,21 @@ private:
         const void* cop[3] = {co[0].data(), co[1].data(), co[2].data()};
         b2s_r1cs* mat = nullptr;
         check(b2s_r1cs_upload(ctx_, mats[0].size(), cs.num_instance_variables(), cs.num_witness_variables(), rpp, colp, cop, &mat));
+        return mat;
+    }
+    b2s_r1cs* upload_lcmap(const ConstraintSystemRef<F>& cs) {
+        const auto& lm = cs->lc_map();
+        const auto& pool = cs->field_interner().vec();
+        const auto it = cs->predicates().find(ark_relations::gr1cs::R1CS_PREDICATE_LABEL);
+        if (it == cs->predicates().end()) throw BackendError(B2S_ERR_INVALID_ARG, "constraint system has no R1CS predicate");
+        const auto& args = it->second.get_constraints();   // argument_lcs[k]: Variable is the raw u64 the ABI takes
+        static_assert(sizeof(ark_relations::gr1cs::Variable) == 8 && sizeof(ark_relations::gr1cs::InternedField) == 4, "ABI layout");
+        const uint64_t* a[3] = {reinterpret_cast<const uint64_t*>(args[0].data()), reinterpret_cast<const uint64_t*>(args[1].data()),
+                                reinterpret_cast<const uint64_t*>(args[2].data())};
+        b2s_r1cs* mat = nullptr;
+        check(b2s_r1cs_upload_lcmap(ctx_, it->second.num_constraints(), cs.num_instance_variables(), cs.num_witness_variables(), a,
+                                    lm.num_lcs(), lm.offsets().data(), reinterpret_cast<const uint64_t*>(lm.vars().data()),
+                                    reinterpret_cast<const uint32_t*>(lm.coeffs().data()), pool.data(), uint32_t(pool.size()), &mat));
         return mat;
     }
     void check(int32_t st) { if (st != B2S_OK) throw BackendError(st, b2s_last_error(ctx_)); }

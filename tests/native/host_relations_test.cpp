@@ -6,6 +6,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <string>
 
 #include "../../snark_b200/host/ark_snark.hpp"
 
@@ -266,6 +267,28 @@ static void cpu_tests(const char* name) {
         CHECK((lc_diff<F>(a, b).terms == T{{one, a}, {minus_one, b}}) && lc_diff<F>(a, a).terms.empty());
         CHECK(LinearCombination<F>::from(Variable::Zero()).terms.empty() && LinearCombination<F>::from(F::zero(), a).terms.empty());
     }
+    {   // test_lc_map_iter_mut (lc_map.rs:524-568) and the interner's conventions (field_interner.rs:27-68)
+        FieldInterner<F> interner;
+        LcMap<F> lcmap;
+        lcmap.push({{U(1), Variable::One()}, {U(2), Variable::instance(2)}}, interner);
+        lcmap.push({{U(3), Variable::witness(4)}, {U(4), Variable::instance(4)}}, interner);
+        lcmap.lc_vars_iter_mut([](Variable* v, Variable* end) {
+            for (; v != end; ++v) if (v->is_instance()) *v = Variable::instance(*v->index() + 1);
+        });
+        std::vector<std::pair<F, Variable>> flattened;
+        for (size_t i = 0; i < lcmap.num_lcs(); i++) for (const auto& t : lcmap.get_lc(i, interner)) flattened.push_back(t);
+        std::vector<std::pair<F, Variable>> expected = {{U(1), Variable::One()}, {U(2), Variable::instance(3)},
+                                                        {U(3), Variable::witness(4)}, {U(4), Variable::instance(5)}};
+        CHECK(flattened == expected);
+        CHECK(lcmap.num_lcs() == 2 && lcmap.total_lc_size() == 4 && (lcmap.offsets() == std::vector<uint64_t>{0, 2, 4}));
+        CHECK(!lcmap.get(2).has_value() && lcmap.get(1)->size() == 2);
+        const F minus_one = F::zero() - one;
+        CHECK(interner.vec()[0] == one && interner.vec()[1] == minus_one);
+        CHECK(interner.get_or_intern(one).id == 0 && interner.get_or_intern(minus_one).id == 1);
+        const uint32_t id7 = interner.get_or_intern(U(7)).id;
+        CHECK(id7 == interner.vec().size() - 1 && interner.get_or_intern(U(7)).id == id7 && *interner.value({id7}) == U(7));
+        CHECK(lcmap.coeffs()[0].id == 0 && !interner.value({1000}).has_value());
+    }
     {   // Sr1csAdapter (sr1cs/mod.rs:122-264): a*b = c  ->  (a+b)^2 = 4c + s, (a-b)^2 = s; instances re-exposed
         DummyCircuit<F> c(U(3), U(5), 8, 8);
         auto cs = ConstraintSystemRef<F>::new_ref();
@@ -353,7 +376,39 @@ static int gpu_prove_rng(const char* circuit) {
     return 0;
 }
 
+// the flat storage of a finalized system, one array per line (compared with oracle/r1cs.py: to_lcmap)
+template <class Curve>
+static void dump_lcmap(const char* tag, bool outlined) {
+    using F = typename Curve::Fr;
+    Circuit2<F> c(F::one(), F::one(), ark_snark::Groth16<Curve>::from_u64(2));
+    auto cs = ConstraintSystemRef<F>::new_ref();
+    c.generate_constraints(cs);
+    if (outlined) cs.set_instance_outliner({R1CS_PREDICATE_LABEL, outline_r1cs<F>});
+    cs.finalize();
+    const auto& lm = cs->lc_map();
+    printf("%s offsets", tag);
+    for (uint64_t o : lm.offsets()) printf(" %llu", (unsigned long long)o);
+    printf("\n%s vars", tag);
+    for (const Variable& v : lm.vars()) printf(" %llu", (unsigned long long)v.raw);
+    printf("\n%s coeffs", tag);
+    for (const InternedField& i : lm.coeffs()) printf(" %u", i.id);
+    printf("\n");
+    for (const F& v : cs->field_interner().vec()) print_words((std::string(tag) + " pool").c_str(), std::vector<uint32_t>(v.v, v.v + F::N));
+    const auto& args = cs->predicates().at(R1CS_PREDICATE_LABEL).get_constraints();
+    for (int k = 0; k < 3; k++) {
+        printf("%s args%d", tag, k);
+        for (const Variable& v : args[k]) printf(" %llu", (unsigned long long)v.raw);
+        printf("\n");
+    }
+}
+
 int main(int argc, char** argv) {
+    if (argc >= 2 && strcmp(argv[1], "lcmap") == 0) {
+        dump_lcmap<b2s::Bls12_381>("bls12_381", false);
+        dump_lcmap<b2s::Bls12_381>("bls12_381-outlined", true);
+        dump_lcmap<b2s::Bn254>("bn254", false);
+        return 0;
+    }
     if (argc >= 2 && strcmp(argv[1], "rng") == 0) {
         auto rng = ark_std::test_rng();
         std::vector<uint32_t> w;
@@ -392,6 +447,6 @@ int main(int argc, char** argv) {
             return 2;
         }
     }
-    printf("usage: %s cpu | rng | gpu-rng <curve 0|1> <circuit2|dummy> | gpu <curve 0|1> <circuit2|dummy> tau alpha beta gamma delta r s\n", argv[0]);
+    printf("usage: %s cpu | rng | lcmap | gpu-rng <curve 0|1> <circuit2|dummy> | gpu <curve 0|1> <circuit2|dummy> tau alpha beta gamma delta r s\n", argv[0]);
     return 64;
 }

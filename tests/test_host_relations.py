@@ -53,6 +53,31 @@ def test_cpp_test_rng_matches_oracle_stream():
             assert got == orng.field_rand_mont(curve.r, 4, ref)
 
 
+def test_cpp_lcmap_storage_matches_oracle_export():
+    """The C++ mirror keeps linear combinations in the reference's flat LcMap + interner (lc_map.rs:51-56,
+    field_interner.rs:13-45); after finalize the arrays -- the input of b2s_r1cs_upload_lcmap -- equal the oracle's
+    `to_lcmap()` export, plain and instance-outlined."""
+    out = subprocess.run([build(), "lcmap"], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stdout + out.stderr
+    got = {}
+    for line in out.stdout.splitlines():
+        tag, field, *vals = line.split()
+        if field == "pool":
+            got.setdefault((tag, field), []).append(sum(int(w, 16) << (32 * i) for i, w in enumerate(vals)))
+        else:
+            got[(tag, field)] = [int(v) for v in vals]
+    for tag, curve, outlined in (("bls12_381", BLS12_381, False), ("bls12_381-outlined", BLS12_381, True), ("bn254", BN254, False)):
+        cs = orc.circuit2(curve, 1, 1, 2)
+        if outlined:
+            cs.set_instance_outliner("R1CS", orc.outline_r1cs)
+        cs.finalize()
+        lm = cs.to_lcmap()
+        assert got[(tag, "offsets")] == lm["offsets"] and got[(tag, "vars")] == lm["vars"] and got[(tag, "coeffs")] == lm["coeffs"], tag
+        R = 1 << 256
+        assert got[(tag, "pool")] == [v * R % curve.r for v in lm["pool"]], tag                 # Montgomery form
+        assert [got[(tag, f"args{k}")] for k in range(3)] == lm["args"], tag
+
+
 def _parse_words(stdout):
     import numpy as np
 
