@@ -72,3 +72,25 @@ def test_lcmap_errors(be):
     with pytest.raises(B2SError) as e:
         upload_lcmap(be, curve, cs)
     assert e.value.code == 16 and "finalize" in str(e.value)
+
+
+@pytest.mark.parametrize("cid,circuit", [(0, "circuit2"), (1, "dummy")])
+def test_cpp_host_proves_through_the_lcmap_path(cid, circuit):
+    """The C++ mirror hands its flat LcMap to b2s_r1cs_upload_lcmap (B2S_HOST_LCMAP=1): same proof as the oracle's."""
+    import subprocess
+
+    from tests.test_host_relations import _parse_words, build
+
+    curve = CURVES[cid]
+    td_vals = [1234567, 31337, 271828, 314159, 161803]
+    rr, ss = 99991, 77773
+    out = subprocess.run([build(), "gpu", str(cid), circuit] + [str(v) for v in td_vals + [rr, ss]], capture_output=True, text=True,
+                         timeout=300, env=dict(os.environ, B2S_HOST_LCMAP="1"))
+    assert out.returncode == 0, out.stdout + out.stderr
+    got = _parse_words(out.stdout)
+    cs = orc.circuit2(curve, 1, 1, 2) if circuit == "circuit2" else orc.dummy_circuit(curve, 3, 5, 16, 16)
+    cs.finalize()
+    mats, inst, wit = cs.to_matrices(), cs.instance_assignment, cs.witness_assignment
+    pk = og.setup(curve, mats, len(inst), len(wit), og.Trapdoor(*td_vals))
+    A, B, C, _ = og.prove(pk, mats, inst, wit, rr, ss)
+    assert (unpack_points(curve, 1, got["A"])[0], unpack_points(curve, 2, got["B"])[0], unpack_points(curve, 1, got["C"])[0]) == (A, B, C)
