@@ -36,3 +36,32 @@ def test_roofline_from_report():
     # a report without MSM kernels still yields a well-formed object
     roof3 = bench.roofline_from_report({"ntt_pass_final<Fr>": (3, 4.5)}, 1 << 24, 1, 24, 6569.6, "measured")
     assert roof3["kernel"] == "ntt_pass_final<Fr>" and roof3["avg_launch_ms"] == 1.5
+
+
+def test_reference_arm_prints_one_contract_line():
+    """`bench.py --impl reference` (the CPU arm the driver runs first): exactly one JSON line on stdout with the
+    contract's keys, `impl: reference`, e2e == value and zero transfer bytes.  Tiny domain so it runs in seconds."""
+    import json
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--log-n", "10", "--ref-log-n", "10",
+                          "--steps", "1", "--warmup", "1"], capture_output=True, text=True, timeout=600, cwd=root)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
+                "dtype", "data", "config", "cpu_baseline", "e2e", "impl"):
+        assert key in d, key
+    assert d["impl"] == "reference" and d["metric"] == "groth16_proofs_per_sec" and d["unit"] == "proofs/s" and d["higher_is_better"] is True
+    assert d["vs_baseline"] is None and d["steps"] == 1 and d["warmup"] == 1 and d["value"] > 0
+    assert d["e2e"] == {"value": d["value"], "unit": "proofs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["value"] == d["value"] and d["cpu_baseline"]["cores"] >= 1
+    assert "workload" in d["config"] and abs(d["ms_per_step"] - 1e3 / d["value"]) < 1e-6 * d["ms_per_step"]
+    # a non-zero rank of a torchrun launch prints nothing
+    quiet = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--log-n", "10", "--ref-log-n", "10",
+                            "--steps", "1", "--warmup", "0"], capture_output=True, text=True, timeout=600, cwd=root,
+                           env=dict(os.environ, RANK="1", WORLD_SIZE="2", LOCAL_RANK="1"))
+    assert quiet.returncode == 0 and quiet.stdout.strip() == ""
