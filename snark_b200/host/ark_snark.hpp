@@ -8,6 +8,8 @@
 // No setup or prover arithmetic runs on the CPU.
 #pragma once
 #include <cstdlib>
+#include <istream>
+#include <ostream>
 #include <stdexcept>
 #include <string>
 #include <utility>
@@ -43,6 +45,63 @@ struct ProvingKey {
 };
 template <class Curve>
 struct Proof { std::vector<uint32_t> a, b, c; };
+
+// A proving key on disk in the layout the backend uploads (Montgomery limbs, affine x||y, zeros = infinity): written once
+// after setup, read back by every prover process -- the reference's "checkpoint" is the serialized key
+// (snark/src/lib.rs:25-36 bounds).  This is the backend's own container, not the ark-serialize encoding (that one is
+// b2s_serialize_*_compressed for points and proofs).  Header: magic, curve id, the three counts, then thirteen
+// length-prefixed arrays in declaration order.  read_proving_key rejects a wrong magic / curve / inconsistent lengths.
+namespace detail {
+constexpr uint64_t PK_MAGIC = 0x31304b5053323042ull;   // "B02SPK01" little-endian
+inline void put_u64(std::ostream& o, uint64_t v) { o.write(reinterpret_cast<const char*>(&v), 8); }
+inline uint64_t get_u64(std::istream& i) {
+    uint64_t v = 0;
+    i.read(reinterpret_cast<char*>(&v), 8);
+    if (!i) throw std::runtime_error("proving key file: truncated");
+    return v;
+}
+inline void put_vec(std::ostream& o, const std::vector<uint32_t>& v) {
+    put_u64(o, v.size());
+    o.write(reinterpret_cast<const char*>(v.data()), std::streamsize(v.size() * 4));
+}
+inline std::vector<uint32_t> get_vec(std::istream& i, uint64_t expect_words, const char* what) {
+    const uint64_t n = get_u64(i);
+    if (n != expect_words) throw std::runtime_error(std::string("proving key file: unexpected length of ") + what);
+    std::vector<uint32_t> v(n);
+    i.read(reinterpret_cast<char*>(v.data()), std::streamsize(n * 4));
+    if (!i) throw std::runtime_error("proving key file: truncated");
+    return v;
+}
+}  // namespace detail
+
+template <class Curve>
+void write_proving_key(std::ostream& o, const ProvingKey<Curve>& pk) {
+    detail::put_u64(o, detail::PK_MAGIC);
+    detail::put_u64(o, uint64_t(Curve::id));
+    detail::put_u64(o, pk.n_instance); detail::put_u64(o, pk.n_witness); detail::put_u64(o, pk.domain_size);
+    for (const auto* v : {&pk.alpha_g1, &pk.beta_g1, &pk.delta_g1, &pk.beta_g2, &pk.delta_g2, &pk.gamma_g2, &pk.gamma_abc_g1, &pk.a_query,
+                          &pk.b_g1_query, &pk.b_g2_query, &pk.h_query, &pk.l_query})
+        detail::put_vec(o, *v);
+    if (!o) throw std::runtime_error("proving key file: write failed");
+}
+
+template <class Curve>
+ProvingKey<Curve> read_proving_key(std::istream& i) {
+    if (detail::get_u64(i) != detail::PK_MAGIC) throw std::runtime_error("proving key file: bad magic");
+    if (detail::get_u64(i) != uint64_t(Curve::id)) throw std::runtime_error("proving key file: written for another curve");
+    ProvingKey<Curve> pk;
+    pk.n_instance = detail::get_u64(i); pk.n_witness = detail::get_u64(i); pk.domain_size = detail::get_u64(i);
+    if (pk.n_instance == 0 || pk.domain_size == 0 || (pk.domain_size & (pk.domain_size - 1)))
+        throw std::runtime_error("proving key file: implausible header");
+    const uint64_t g1 = 2 * Curve::Fq::N, g2 = 4 * Curve::Fq::N, n_vars = pk.n_instance + pk.n_witness;
+    pk.alpha_g1 = detail::get_vec(i, g1, "alpha_g1"); pk.beta_g1 = detail::get_vec(i, g1, "beta_g1"); pk.delta_g1 = detail::get_vec(i, g1, "delta_g1");
+    pk.beta_g2 = detail::get_vec(i, g2, "beta_g2"); pk.delta_g2 = detail::get_vec(i, g2, "delta_g2"); pk.gamma_g2 = detail::get_vec(i, g2, "gamma_g2");
+    pk.gamma_abc_g1 = detail::get_vec(i, pk.n_instance * g1, "gamma_abc_g1");
+    pk.a_query = detail::get_vec(i, n_vars * g1, "a_query"); pk.b_g1_query = detail::get_vec(i, n_vars * g1, "b_g1_query");
+    pk.b_g2_query = detail::get_vec(i, n_vars * g2, "b_g2_query"); pk.h_query = detail::get_vec(i, (pk.domain_size - 1) * g1, "h_query");
+    pk.l_query = detail::get_vec(i, pk.n_witness * g1, "l_query");
+    return pk;
+}
 
 template <class Curve>
 class Groth16 {

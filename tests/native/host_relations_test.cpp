@@ -6,6 +6,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <sstream>
 #include <string>
 
 #include "../../snark_b200/host/ark_snark.hpp"
@@ -288,6 +289,31 @@ static void cpu_tests(const char* name) {
         const uint32_t id7 = interner.get_or_intern(U(7)).id;
         CHECK(id7 == interner.vec().size() - 1 && interner.get_or_intern(U(7)).id == id7 && *interner.value({id7}) == U(7));
         CHECK(lcmap.coeffs()[0].id == 0 && !interner.value({1000}).has_value());
+    }
+    {   // proving key container: round trip, and rejection of a wrong curve / truncated / inconsistent file
+        ark_snark::ProvingKey<Curve> pk;
+        pk.n_instance = 2; pk.n_witness = 3; pk.domain_size = 8;
+        const size_t g1 = 2 * Curve::Fq::N, g2 = 4 * Curve::Fq::N;
+        uint32_t ctr = 1;
+        auto fill = [&](std::vector<uint32_t>& v, size_t words) { v.resize(words); for (auto& w : v) w = ctr++ * 2654435761u; };
+        fill(pk.alpha_g1, g1); fill(pk.beta_g1, g1); fill(pk.delta_g1, g1); fill(pk.beta_g2, g2); fill(pk.delta_g2, g2); fill(pk.gamma_g2, g2);
+        fill(pk.gamma_abc_g1, 2 * g1); fill(pk.a_query, 5 * g1); fill(pk.b_g1_query, 5 * g1); fill(pk.b_g2_query, 5 * g2);
+        fill(pk.h_query, 7 * g1); fill(pk.l_query, 3 * g1);
+        std::stringstream file;
+        ark_snark::write_proving_key(file, pk);
+        const std::string bytes = file.str();
+        auto back = ark_snark::read_proving_key<Curve>(file);
+        CHECK(back.n_instance == 2 && back.n_witness == 3 && back.domain_size == 8 && back.h_query == pk.h_query && back.b_g2_query == pk.b_g2_query);
+        CHECK(back.alpha_g1 == pk.alpha_g1 && back.gamma_abc_g1 == pk.gamma_abc_g1 && back.l_query == pk.l_query && back.gamma_g2 == pk.gamma_g2);
+        auto rejects = [&](std::string b) { std::stringstream f(b); try { ark_snark::read_proving_key<Curve>(f); } catch (const std::runtime_error&) { return true; } return false; };
+        CHECK(rejects(bytes.substr(0, bytes.size() - 5)));                    // truncated
+        std::string other = bytes; other[8] ^= 1;                             // curve id flipped
+        CHECK(rejects(other));
+        std::string magic = bytes; magic[0] ^= 0x40;
+        CHECK(rejects(magic));
+        std::string counts = bytes; counts[24] ^= 1;                          // n_witness 3 -> 2: array lengths no longer match
+        CHECK(rejects(counts));
+        CHECK(!rejects(bytes));
     }
     {   // Sr1csAdapter (sr1cs/mod.rs:122-264): a*b = c  ->  (a+b)^2 = 4c + s, (a-b)^2 = s; instances re-exposed
         DummyCircuit<F> c(U(3), U(5), 8, 8);
