@@ -4,6 +4,9 @@
 Two kinds of vectors:
   * reference_matrices.json -- TRANSCRIBED from the reference's own tests (the only golden vectors the reference
     holds for this path): gr1cs/tests/circuit2.rs:21-43, circuit1.rs:28-61, tests/mod.rs:19-33,57-71,138-142.
+  * host_vectors.json -- host-side formats, produced by the oracle: the flat LcMap arrays of the finalized circuit2 (the
+    input of b2s_r1cs_upload_lcmap), the first words / Fr draws of the restated `ark_std::test_rng()` stream (the ChaCha
+    core under it is pinned by published keystreams in tests/test_oracle_rng.py), and circuit2's compressed VerifyingKey.
   * oracle_vectors.json -- produced by the pure-Python oracle (oracle/*.py) with fixed seeds: NTT / coset NTT,
     MSM G1/G2, witness_map and a full Groth16 proof (known trapdoor), compressed proof bytes.  The reference cannot
     be run here (Rust, no toolchain), so these pin the oracle against regressions and give the GPU tests fixed
@@ -83,7 +86,31 @@ def oracle_vectors():
     return out
 
 
+def host_vectors():
+    from oracle import rng as orng
+
+    out = {}
+    for curve in (BLS12_381, BN254):
+        cs = orc.circuit2(curve, 1, 1, 2)
+        cs.finalize()
+        lm = cs.to_lcmap()
+        v = {"lcmap_circuit2": {"offsets": lm["offsets"], "vars": [H(x) for x in lm["vars"]], "coeffs": lm["coeffs"],
+                                "pool": [H(x) for x in lm["pool"]], "args": [[H(x) for x in a] for a in lm["args"]]}}
+        rng = orng.test_rng()
+        v["test_rng_fr"] = [H(orng.fr_rand(curve, rng)) for _ in range(4)]
+        mats, inst, wit = cs.to_matrices(), cs.instance_assignment, cs.witness_assignment
+        pk = og.setup(curve, mats, len(inst), len(wit), og.Trapdoor(3, 5, 7, 11, 13))
+        vk = {"alpha_g1": pk.alpha_g1, "beta_g2": pk.beta_g2, "gamma_g2": pk.gamma_g2, "delta_g2": pk.delta_g2, "gamma_abc_g1": pk.gamma_abc_g1}
+        v["vk_circuit2_trapdoor_3_5_7_11_13_compressed"] = oser.verifying_key_bytes(curve, vk, True).hex()
+        out[curve.name] = v
+    rng = orng.test_rng()
+    out["test_rng_words"] = [H(rng.next_u32()) for _ in range(16)]
+    return out
+
+
 if __name__ == "__main__":
+    with open(os.path.join(HERE, "host_vectors.json"), "w") as f:
+        json.dump(host_vectors(), f, indent=1)
     with open(os.path.join(HERE, "reference_matrices.json"), "w") as f:
         json.dump(reference_matrices(), f, indent=1)
     with open(os.path.join(HERE, "oracle_vectors.json"), "w") as f:
