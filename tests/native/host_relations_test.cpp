@@ -122,6 +122,30 @@ static void cpu_tests(const char* name) {
         auto t = transpose(golden[1], 4);
         CHECK(t[1].size() == 2 && t[2].size() == 3 && t[0].empty());
     }
+    {   // Setup mode builds the same matrices without evaluating a single assignment closure (what circuit_specific_setup uploads)
+        Circuit2<F> c(one, one, two);
+        auto prove_cs = ConstraintSystemRef<F>::new_ref();
+        prove_cs.set_optimization_goal(OptimizationGoal::Constraints);
+        c.generate_constraints(prove_cs);
+        prove_cs.finalize();
+        auto setup_cs = ConstraintSystemRef<F>::new_ref();
+        setup_cs.set_optimization_goal(OptimizationGoal::Constraints);
+        setup_cs.set_mode(SynthesisMode::Setup());
+        c.generate_constraints(setup_cs);
+        setup_cs.finalize();
+        CHECK(setup_cs.to_matrices() == prove_cs.to_matrices());
+        CHECK(setup_cs.num_witness_variables() == 2 && setup_cs.num_instance_variables() == 2 && setup_cs.num_constraints() == 3);
+        CHECK(setup_cs->lc_map().offsets() == prove_cs->lc_map().offsets() && setup_cs->lc_map().vars() == prove_cs->lc_map().vars());
+        DummyCircuit<F> d(U(3), U(5), 16, 16);
+        auto ds = ConstraintSystemRef<F>::new_ref();
+        ds.set_mode(SynthesisMode::Setup());
+        d.generate_constraints(ds);
+        ds.finalize();
+        auto dp = ConstraintSystemRef<F>::new_ref();
+        d.generate_constraints(dp);
+        dp.finalize();
+        CHECK(ds.to_matrices() == dp.to_matrices());
+    }
     {   // unsatisfied witness is reported at the first failing constraint
         Circuit2<F> c(one, one, U(3));
         auto cs = ConstraintSystemRef<F>::new_ref();
