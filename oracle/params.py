@@ -20,7 +20,7 @@ All constants here were re-derived or checked numerically (see
 tests/test_oracle_fields.py): primality is not re-proved, but generator
 order, curve membership and two-adicity are.
 """
-from dataclasses import dataclass, field
+from dataclasses import dataclass
 from typing import Tuple
 
 

@@ -11,7 +11,6 @@ import pytest
 
 from oracle import groth16 as og
 from oracle import r1cs as orc
-from oracle.ec import groups
 from oracle.params import BLS12_381, BN254
 from tests.util import unpack_points
 

@@ -2,7 +2,6 @@
 oracle, which is itself pinned by the definitions in tests/test_oracle_py.py."""
 import random
 
-import numpy as np
 import pytest
 
 from oracle import cnative
