@@ -31,6 +31,25 @@ def test_curve_constants(curve):
         assert w == 0x16A2A19EDFE81F20D09B681922C813B4B63683508C2280B93829971F439F0D2B
 
 
+def test_published_bn254_doubling_vector():
+    """A known answer from outside this repository: 2 * (1, 2) on alt_bn128, the EIP-196 ecAdd / ecMul test vector."""
+    G1 = groups(BN254)[0]
+    expect = (0x030644E72E131A029B85045B68181585D97816A916871CA8D3C208C16D87CFD3,
+              0x15ED738C0E0A7C92E7845F96B2AE9C0A68A6A449E3538FC7FF3EBF7A5A18A2C4)
+    assert G1.mul(G1.gen, 2) == expect and G1.add(G1.gen, G1.gen) == expect
+    assert expect == (1368015179489954701390400359078579693043519447331113978918064868415326638035,
+                      9918110051302171585080402603319702774565515993150576347155970296011118125764)
+
+
+def test_published_bls12_381_doubling_vector():
+    """2 * G1 in the zcash compressed form, as it appears in the BLS12-381 test suites of other libraries."""
+    from oracle import serialize as oser
+
+    G1 = groups(BLS12_381)[0]
+    assert oser.point_compressed(BLS12_381, 1, G1.mul(G1.gen, 2)).hex() == (
+        "a572cbea904d67468808c8eb50a9450c9721db309128012543902d0ac358a62ae28f75bb8f1c7c42c39a8c5529bf0f4e")
+
+
 def test_reference_golden_circuit2():
     """test_circuit2_matrices (gr1cs/tests/mod.rs:136-147): matrices after finalize == circuit2.rs:21-43."""
     cs = orc.circuit2(BLS12_381, 1, 1, 2)
