@@ -29,6 +29,8 @@ def test_curve_constants(curve):
     assert pow(curve.fr_generator, (curve.r - 1) // 2, curve.r) == curve.r - 1   # generator is a non-residue
     if curve is BLS12_381:  # SURVEY Appendix B value
         assert w == 0x16A2A19EDFE81F20D09B681922C813B4B63683508C2280B93829971F439F0D2B
+    else:                   # the 2^28-th root of unity published with ark-bn254 / snarkjs (5^((r-1)/2^28))
+        assert w == 19103219067921713944291392827692070036145651957329286315305642004821462161904
 
 
 def test_published_bn254_doubling_vector():
