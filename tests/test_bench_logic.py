@@ -38,6 +38,13 @@ def test_roofline_from_report():
     assert roof3["kernel"] == "ntt_pass_final<Fr>" and roof3["avg_launch_ms"] == 1.5
 
 
+def test_cpu_sample_scaling_follows_the_reference_add_count():
+    """A 2^20 sample stands for 7.2 % of a 2^24 proof, not 1/16: bigger MSMs use fewer window passes per point."""
+    assert bench.cpu_scale(24, 24) == 1.0
+    assert abs(bench.cpu_scale(20, 24) - (17 * (2**20 + 2**15)) / (15 * (2**24 + 2**18))) < 1e-12
+    assert 1 / 16 < bench.cpu_scale(20, 24) < 1 / 13 and 1 / 256 < bench.cpu_scale(16, 24) < 1 / 128
+
+
 def test_reference_arm_prints_one_contract_line():
     """`bench.py --impl reference` (the CPU arm the driver runs first): exactly one JSON line on stdout with the
     contract's keys, `impl: reference`, e2e == value and zero transfer bytes.  Tiny domain so it runs in seconds."""
