@@ -553,6 +553,19 @@ int orc_groth16_prove(int curve, const uint64_t* const row_ptr[3], const uint32_
     return 0;
 }
 
+// h = witness_map(A, B, C, z) alone (SpMV + 7 transforms + quotient), z = instance || witness: the full-size parity
+// tests compare the GPU's h with it element by element (2^24 / 2^25 domains take seconds on the host cores)
+int orc_witness_map(int curve, const uint64_t* const row_ptr[3], const uint32_t* const col[3], const void* const coeff[3],
+                    uint64_t n_rows, uint64_t n_inst, const void* z, int log_dom, void* out_h, int threads) {
+    init_all();
+    Csr mats[3];
+    for (int k = 0; k < 3; k++) mats[k] = Csr{row_ptr[k], col[k], coeff[k]};
+    if (curve == 0) witness_map(mats, n_rows, n_inst, (const BlsFr*)z, log_dom, (BlsFr*)out_h, g_bls_fr, threads);
+    else if (curve == 1) witness_map(mats, n_rows, n_inst, (const BnFr*)z, log_dom, (BnFr*)out_h, g_bn_fr, threads);
+    else return 1;
+    return 0;
+}
+
 // out[i] = (start + i) * gen, affine
 int orc_multiples(int curve, int group, const void* gen, uint64_t start, uint64_t n, void* out, int threads) {
     init_all();

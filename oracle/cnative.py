@@ -25,6 +25,8 @@ def load(build=True):
         lib.orc_spmv.argtypes = [c_int, c_void_p, c_void_p, c_void_p, c_uint64, c_void_p, c_void_p, c_int]
         lib.orc_groth16_prove.argtypes = [c_int, POINTER(c_void_p), POINTER(c_void_p), POINTER(c_void_p), c_uint64, c_uint64,
                                           c_uint64, POINTER(c_void_p)] + [c_void_p] * 8 + [c_int]
+        lib.orc_witness_map.argtypes = [c_int, POINTER(c_void_p), POINTER(c_void_p), POINTER(c_void_p), c_uint64, c_uint64, c_void_p, c_int,
+                                        c_void_p, c_int]
         lib.orc_multiples.argtypes = [c_int, c_int, c_void_p, c_uint64, c_uint64, c_void_p, c_int]
         lib.orc_fr_dot.argtypes = [c_int, c_void_p, c_void_p, c_uint64, c_void_p]
         _lib = lib
@@ -86,6 +88,18 @@ def groth16_prove(curve_id, csr3, n_rows, n_inst, n_wit, pk_arrays, z_inst, z_wi
                                   _p(a), _p(b), _p(c), _p(h), threads or threads_default())
     assert rc == 0
     return a, b, c, h
+
+
+def witness_map(curve_id, csr3, n_rows, n_inst, z, threads=None):
+    """h of the LibsnarkReduction for z = instance || witness; domain = next_pow2(n_rows + n_inst)."""
+    rp = (c_void_p * 3)(*[_p(m[0]) for m in csr3])
+    col = (c_void_p * 3)(*[_p(m[1]) for m in csr3])
+    co = (c_void_p * 3)(*[_p(m[2]) for m in csr3])
+    log_dom = max((n_rows + n_inst - 1).bit_length(), 0)
+    h = np.zeros((1 << log_dom) * 8, dtype=np.uint32)
+    rc = load().orc_witness_map(curve_id, rp, col, co, n_rows, n_inst, _p(z), log_dom, _p(h), threads or threads_default())
+    assert rc == 0
+    return h
 
 
 def multiples(curve_id, group, gen, start, n, threads=None):

@@ -55,6 +55,13 @@ int32_t b2s_ctx_create(int32_t curve_id, int32_t device_ordinal, b2s_ctx** out) 
         delete c;
         return B2S_ERR_CUDA;
     }
+    // gathers of 96-byte points: a 32-byte L2 fetch granularity (instead of the default 64) avoids fetching bytes
+    // next to a randomly addressed point (a hint; B2S_L2_GRAN overrides, 0 leaves the driver default)
+    {
+        const char* g = getenv("B2S_L2_GRAN");
+        const long gran = g ? strtol(g, nullptr, 10) : 0;
+        if (gran > 0) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)gran);
+    }
     // keep freed blocks in the stream-ordered pool: proofs reuse the same multi-GiB scratch every call
     cudaMemPool_t pool;
     if (cudaDeviceGetDefaultMemPool(&pool, device_ordinal) == cudaSuccess) {

@@ -89,6 +89,7 @@ struct DevBuf {
     Ctx* ctx = nullptr;
     void* p = nullptr;
     size_t bytes = 0;
+    bool secret = false;   // holds trapdoor-derived scalars: cleared before the block returns to the pool
     DevBuf() = default;
     DevBuf(const DevBuf&) = delete;
     DevBuf& operator=(const DevBuf&) = delete;
@@ -107,6 +108,7 @@ struct DevBuf {
         return B2S_OK;
     }
     void release() {
+        if (p && secret) cudaMemsetAsync(p, 0, bytes, ctx->stream);
         if (p) cudaFreeAsync(p, ctx->stream);
         p = nullptr;
         bytes = 0;
@@ -128,6 +130,21 @@ struct InBuf {
     }
     template <class T>
     const T* as() const { return reinterpret_cast<const T*>(dptr); }
+};
+
+// Kernels that need more than 48 KiB of dynamic shared memory: the attribute is per device, so it is (re)applied
+// on every launch path rather than cached in a process-wide flag (a second ctx on another GPU needs it too).
+#define B2S_SMEM_ATTR(ctx, kern, bytes) \
+    B2S_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes)))
+
+// clears a host object holding secrets when the scope ends, whichever way it ends
+struct HostWipe {
+    void* p;
+    size_t n;
+    ~HostWipe() {
+        volatile unsigned char* q = reinterpret_cast<volatile unsigned char*>(p);
+        for (size_t i = 0; i < n; i++) q[i] = 0;
+    }
 };
 
 inline unsigned cdiv(uint64_t a, uint64_t b) { return (unsigned)((a + b - 1) / b); }

@@ -155,6 +155,17 @@ static int32_t shard_t(Ctx* c, const b2s_pk* pk, const b2s_r1cs* m, const void* 
     B2S_TRY(z.alloc(c, (n_vars + 2) * sizeof(Fr)));
     B2S_TRY(h.alloc(c, N * sizeof(Fr)));
     B2S_TRY(tails.alloc(c, 4 * 64 * sizeof(P1) + 64 * sizeof(P2)));
+    // Horner tails run on c->aux and read `tails` / write the outputs: whatever way this function is left, the aux
+    // stream must be done before the buffers above (and the caller's outputs) go back to the pool
+    struct AuxGuard {
+        Ctx* c;
+        ~AuxGuard() {
+            if (c->aux_pending) {
+                cudaStreamSynchronize(c->aux);
+                c->aux_pending = false;
+            }
+        }
+    } aux_guard{c};
     Fr* zd = z.as<Fr>();
     if (z_dev) {
         B2S_CUDA(c, cudaMemcpyAsync(zd, z_dev, n_vars * sizeof(Fr), cudaMemcpyDeviceToDevice, c->stream));

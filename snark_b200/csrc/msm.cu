@@ -57,7 +57,10 @@ struct DigitIter {
 template <class Fr>
 __device__ __forceinline__ void load_scalar(DigitIter& it, const Fr* scalars, uint64_t i, bool mont) {
     Fr s = ld_struct(scalars + i);
-    if (mont) s = s.from_mont();
+    // canonical input may be any 256-bit value (the ABI does not promise < r): to_mont / from_mont leaves s mod r, so a
+    // top-window digit can never index past the bucket arrays
+    if (!mont) s = s.to_mont();
+    s = s.from_mont();
 #pragma unroll
     for (int j = 0; j < 8; j++) it.k[j] = s.v[j];
     it.carry = 0;
@@ -474,36 +477,81 @@ static int32_t msm_run_t(Ctx* c, const void* bases_dev, const void* scalars_dev,
     B2S_LAUNCH(c, msm_scan_apply_kernel, ntiles, SCAN_THREADS, 0, counts, no_perm, sh, tiles.as<Scan3>(), offsets, task_off, heavy);
     B2S_LAUNCH(c, msm_scatter_kernel<Fr>, cdiv(n, 256), 256, 0, scalars, n, mont, sh, offsets, cursor, sorted.as<uint32_t>());
     constexpr bool is_g1 = sizeof(F) == sizeof(typename Curve::Fq);
-    // optional batched-affine halving rounds (msm_affine.cuh); afterwards the points are already in bucket order
-    // On for big problems only: at 2^24 points three rounds with K = 512 take 10-13 % off skewed-scalar MSMs (G1 89 -> 79
-    // ms, G2 276 -> 239 ms) and are neutral on uniform ones; below ~2^23 points the rounds do not fill the GPU at
-    // that K.  (profiles/r01_experiments.md)
-    const uint32_t ba_rounds = env_u32("B2S_MSM_AFFINE_ROUNDS", (uint64_t)sh.nwin * n >= (1ull << 27) ? 3u : 0u);
-    const uint32_t ba_k = max(1u, env_u32("B2S_MSM_AFFINE_K", 512));
+    // batched-affine halving rounds (msm_affine.cuh); afterwards the points are already in bucket order.
+    // Rounds are worth it when buckets hold several points: R = ceil(log2(points per bucket)) rounds leave <= 2 points
+    // per average bucket for the XYZZ kernel; heavy buckets (skewed scalars) shrink by 2^R as well.
+    uint32_t ba_auto = 0;
+    {
+        const uint64_t per_bucket = ((uint64_t)sh.nwin * n) / sh.G;
+        while ((1ull << ba_auto) < per_bucket) ba_auto++;
+        if ((uint64_t)sh.nwin * n < (1ull << 16)) ba_auto = 0;            // tiny problems: launch overhead only
+    }
+    uint32_t ba_rounds = env_u32("B2S_MSM_AFFINE_ROUNDS", ba_auto);
+    // scratch of the rounds: two output buffers, the prefix products and the lane totals (bounded by the first round)
+    {
+        const uint64_t t0 = ((uint64_t)sh.nwin * n + sh.G) / 2 + 1;
+        const uint64_t need = t0 * (sizeof(Affine<F>) * 3 / 2 + sizeof(F)) + t0 / 4;
+        size_t free_b = 0, total_b = 0;
+        cudaMemGetInfo(&free_b, &total_b);
+        uint64_t pool_held = 0;
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, c->device) == cudaSuccess) {
+            uint64_t reserved = 0, used = 0;
+            cudaMemPoolGetAttribute(pool, cudaMemPoolAttrReservedMemCurrent, &reserved);
+            cudaMemPoolGetAttribute(pool, cudaMemPoolAttrUsedMemCurrent, &used);
+            pool_held = reserved > used ? reserved - used : 0;
+        }
+        if (ba_rounds && need + ((uint64_t)2 << 30) > (uint64_t)free_b + pool_held && !getenv("B2S_MSM_AFFINE_ROUNDS")) ba_rounds = 0;
+    }
     const void* acc_bases = bases;
     const uint32_t* acc_sorted = sorted.as<uint32_t>();
     const uint32_t* acc_offsets = offsets;
-    DevBuf ba_ints, ba_out[2], ba_prefix;
+    DevBuf ba_ints, ba_out[2], ba_prefix, ba_tot, ba_bits;
     if (ba_rounds) {
         B2S_TRY(ba_ints.alloc(c, ((size_t)2 * sh.G + 1) * sizeof(uint32_t)));
         uint32_t* cnt[2] = {counts, ba_ints.as<uint32_t>()};
         uint32_t* off[2] = {offsets, ba_ints.as<uint32_t>() + sh.G};
         uint64_t t_in = (uint64_t)sh.nwin * n;
+        const uint64_t out_bound0 = (t_in + sh.G) / 2 + 1;
+        const uint64_t words_bound0 = out_bound0 / 32 + 2;
+        const uint64_t tot_bound = (words_bound0 / BA_KMIN + 2) * 32;
+        const uint32_t rank_tiles0 = cdiv(words_bound0, BA_SCAN_TILE);
+        // bitmap | wrank | rank tile sums
+        B2S_TRY(ba_bits.alloc(c, (2 * words_bound0 + rank_tiles0 + 1) * sizeof(uint32_t)));
+        uint32_t* bitmap = ba_bits.as<uint32_t>();
+        uint32_t* wrank = bitmap + words_bound0;
+        uint32_t* rtiles = wrank + words_bound0;
+        B2S_TRY(ba_prefix.alloc(c, out_bound0 * sizeof(F)));
+        B2S_TRY(ba_tot.alloc(c, 2 * tot_bound * sizeof(F)));
+        const uint32_t target_units = 4u * 12u * (uint32_t)c->sm_count;
+        // the two ping-pong output buffers, sized for the rounds that use them (even rounds write [1], odd rounds [0])
+        B2S_TRY(ba_out[1].alloc(c, out_bound0 * sizeof(Affine<F>)));
+        if (ba_rounds > 1) B2S_TRY(ba_out[0].alloc(c, ((out_bound0 + sh.G) / 2 + 1) * sizeof(Affine<F>)));
         int cur = 0;
         const void* prev = nullptr;
         for (uint32_t r = 0; r < ba_rounds; r++) {
             const int nxt = cur ^ 1;
             const uint64_t out_bound = (t_in + sh.G) / 2 + 1;
+            const uint32_t n_words = (uint32_t)(out_bound / 32 + 2);
+            const uint32_t rank_tiles = cdiv(n_words, BA_SCAN_TILE);
             B2S_LAUNCH(c, msm_ba_halve_kernel, cdiv(sh.G, 256), 256, 0, cnt[cur], sh.G, cnt[nxt]);
             B2S_LAUNCH(c, msm_scan_tiles_kernel, ntiles, SCAN_THREADS, 0, cnt[nxt], no_perm, sh, tiles.as<Scan3>());
             B2S_LAUNCH(c, msm_scan_spine_kernel, 1, 1024, 0, tiles.as<Scan3>(), ntiles, sh, off[nxt], task_off, heavy);
             B2S_LAUNCH(c, msm_scan_apply_kernel, ntiles, SCAN_THREADS, 0, cnt[nxt], no_perm, sh, tiles.as<Scan3>(), off[nxt], task_off, heavy);
-            B2S_TRY(ba_out[nxt].alloc(c, out_bound * sizeof(Affine<F>)));
-            B2S_TRY(ba_prefix.alloc(c, out_bound * sizeof(F)));
-            if (is_g1) B2S_TRY(msm_ba_round_g1(c, r == 0, bases, sorted.as<uint32_t>(), prev, off[cur], off[nxt], sh.G, ba_k, out_bound, ba_prefix.p, ba_out[nxt].p));
-            else B2S_TRY(msm_ba_round_g2(c, r == 0, bases, sorted.as<uint32_t>(), prev, off[cur], off[nxt], sh.G, ba_k, out_bound, ba_prefix.p, ba_out[nxt].p));
+            B2S_CUDA(c, cudaMemsetAsync(bitmap, 0, (size_t)n_words * sizeof(uint32_t), c->stream));
+            B2S_LAUNCH(c, msm_ba_singles_kernel, cdiv(sh.G, 256), 256, 0, cnt[cur], off[nxt], sh.G, bitmap);
+            B2S_LAUNCH(c, msm_ba_rank_tiles_kernel, rank_tiles, BA_SCAN_THREADS, 0, bitmap, n_words, rtiles);
+            B2S_LAUNCH(c, msm_ba_rank_spine_kernel, 1, 1024, 0, rtiles, rank_tiles);
+            B2S_LAUNCH(c, msm_ba_rank_apply_kernel, rank_tiles, BA_SCAN_THREADS, 0, bitmap, n_words, rtiles, wrank);
+            BaRoundArgs ra{};
+            ra.first = r == 0;
+            ra.bases = bases; ra.sorted = sorted.as<uint32_t>(); ra.prev = prev;
+            ra.bitmap = bitmap; ra.wrank = wrank; ra.t_out = off[nxt] + sh.G;
+            ra.target_units = target_units;
+            ra.prefix = ba_prefix.p; ra.tot = ba_tot.p; ra.inv_scratch = ba_tot.as<F>() + tot_bound; ra.out = ba_out[nxt].p;
+            if (is_g1) B2S_TRY(msm_ba_round_g1(c, ra));
+            else B2S_TRY(msm_ba_round_g2(c, ra));
             prev = ba_out[nxt].p;
-            ba_out[cur].release();
             t_in = out_bound;
             cur = nxt;
         }
@@ -532,15 +580,9 @@ static int32_t msm_run_t(Ctx* c, const void* bases_dev, const void* scalars_dev,
     if (is_g1) B2S_TRY(msm_accumulate_g1(c, acc_bases, acc_sorted, acc_offsets, task_off, perm, sh, bucket_acc.p, partials.p));
     else B2S_TRY(msm_accumulate_g2(c, acc_bases, acc_sorted, acc_offsets, task_off, perm, sh, bucket_acc.p, partials.p));
     const size_t red_smem = (size_t)MSM_RED_THREADS * sizeof(Pt);
-    static bool attr_done[2][2] = {{false, false}, {false, false}};
-    constexpr int gi = sizeof(F) == sizeof(typename Curve::Fq) ? 0 : 1;
-    if (!attr_done[Curve::id][gi]) {
-        B2S_CUDA(c, cudaFuncSetAttribute(msm_reduce_heavy_kernel<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)red_smem));
-        B2S_CUDA(c, cudaFuncSetAttribute(msm_reduce_heavy_stage1_kernel<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)red_smem));
-        B2S_CUDA(c, cudaFuncSetAttribute(msm_window_sum_kernel<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)red_smem));
-        B2S_CUDA(c, cudaFuncSetAttribute(group_sum_affine_kernel<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)red_smem));
-        attr_done[Curve::id][gi] = true;
-    }
+    B2S_SMEM_ATTR(c, msm_reduce_heavy_kernel<F>, red_smem);
+    B2S_SMEM_ATTR(c, msm_reduce_heavy_stage1_kernel<F>, red_smem);
+    B2S_SMEM_ATTR(c, msm_window_sum_kernel<F>, red_smem);
     B2S_LAUNCH(c, msm_reduce_heavy_stage1_kernel<F>, 4 * c->sm_count, MSM_RED_THREADS, red_smem, heavy, task_off,
                partials.as<Pt>(), heavy_tmp.as<Pt>());
     B2S_LAUNCH(c, msm_reduce_heavy_kernel<F>, 2 * c->sm_count, MSM_RED_THREADS, red_smem, heavy, task_off, perm,

@@ -111,8 +111,9 @@ msm_accumulate_kernel(const Affine<F>* __restrict__ bases, const uint32_t* __res
 
     XYZZ<F> acc = XYZZ<F>::identity();
     for (uint32_t pos = beg; pos < end; pos++) {
-        const uint32_t e = sorted ? sorted[pos] : pos;   // sorted == nullptr: bases are already in bucket order
-        Affine<F> q = ld_struct(bases + (e & 0x7fffffffu));
+        // sorted == nullptr: the bases are already in bucket order (output of the batched-affine rounds), no sign bit
+        const uint32_t e = sorted ? sorted[pos] : 0u;
+        Affine<F> q = ld_struct(bases + (sorted ? (e & 0x7fffffffu) : pos));
         if (e >> 31) q.y = q.y.neg();
         madd(acc, q);
     }

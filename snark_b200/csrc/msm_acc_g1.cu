@@ -25,11 +25,10 @@ int32_t msm_horner_g1(Ctx* c, cudaStream_t st, const void* wins, MsmShape sh, vo
     });
 }
 
-int32_t msm_ba_round_g1(Ctx* c, bool first, const void* bases, const uint32_t* sorted, const void* prev, const uint32_t* in_off,
-                        const uint32_t* out_off, uint32_t G, uint32_t K, uint64_t out_bound, void* prefix, void* out) {
+int32_t msm_ba_round_g1(Ctx* c, const BaRoundArgs& a) {
     return dispatch_curve(c, [&](auto curve) {
         using F = typename decltype(curve)::Fq;
-        return msm_ba_round_launch<F>(c, "msm_ba_round_g1", first, bases, sorted, prev, in_off, out_off, G, K, out_bound, prefix, out);
+        return msm_ba_round_launch<F>(c, "msm_ba_p1_g1", "msm_ba_inv_g1", "msm_ba_p2_g1", a);
     });
 }
 

@@ -1,197 +1,488 @@
-// Batched-affine pairwise reduction rounds in front of the XYZZ bucket accumulation.
+// Batched-affine pairwise reduction rounds in front of the XYZZ bucket accumulation (step 3b of msm.cu).
 //
-// A round halves every bucket: the points of a bucket (contiguous in the bucket-sorted order) are added
-// in adjacent pairs IN AFFINE coordinates; all pairs of a round are independent, so each thread takes K
-// consecutive outputs and shares ONE field inversion among them (Montgomery's trick):
-//   pass 1  d_i = x2 - x1 (or 2 y1 when doubling, 1 when nothing is to be inverted), prefix products to scratch
-//   invert  the product of the K denominators
-//   pass 2  backwards: 1/d_i from the running inverse and the stored prefix, lambda = num_i / d_i,
-//           x3 = lambda^2 - x1 - x2,  y3 = lambda (x1 - x3) - y1
-// i.e. 6 multiplications per addition plus inverse/K, against 10 for the XYZZ mixed addition (Fq2: 17 vs 28
-// base multiplications).  The price is HBM traffic (points are read twice, prefixes written and read) -- the
-// resource this ALU-bound path leaves idle.  After R rounds every bucket holds ceil(n / 2^R) points and the
-// XYZZ kernel (msm_acc.cuh) finishes.  All special cases keep the result an exact group element:
-// missing partner / infinity -> copy, P + P -> tangent, P + (-P) -> infinity.
+// A round halves every bucket: the points of a bucket (contiguous in the bucket-sorted order) are added in
+// adjacent pairs IN AFFINE coordinates,  lambda = (y2 - y1) / (x2 - x1),  x3 = lambda^2 - x1 - x2,
+// y3 = lambda (x1 - x3) - y1.  All pairs of a round are independent, so the divisions share inversions
+// (Montgomery's trick): 6 multiplications per addition instead of the 10 of an XYZZ mixed addition (Fq2: 17 base
+// multiplications instead of 28).  After R rounds every bucket holds ceil(n / 2^R) points and the XYZZ kernel
+// (msm_acc.cuh) finishes.  All special cases keep the result an exact group element: missing partner /
+// infinity -> copy, P + P -> tangent, P + (-P) -> infinity.
+//
+// Work decomposition (this is what makes the round ALU-bound instead of latency-bound, profiles/r02_*):
+//   * outputs of a round are numbered 0 .. T_out-1 in bucket order; 32 consecutive outputs form a ROW, lane l of
+//     a warp owns output 32 q + l of row q, K consecutive rows form a UNIT (one warp, one inversion chain per
+//     lane).  Work per unit is the same whatever the bucket sizes, so all-equal witnesses (one bucket per window
+//     holding every point, relations/src/sr1cs/mod.rs:306-309) and uniform scalars run at the same rate.
+//   * where an output's inputs sit follows from one bit per output: `single` = last output of a bucket with an
+//     odd count (it has no partner).  inputs of output o = positions 2 o - rank(o) and +1, rank(o) = number of
+//     single outputs before o = wrank[q] + popc(bitmap[q] & lanes below).  No per-thread bucket walk.
+//   * pass 1 (msm_ba_p1_kernel): per lane, prefix products of the denominators d = x2 - x1 down its K rows
+//     (x coordinates only), prefix to HBM (coalesced), lane total to tot[].
+//   * inversion (msm_ba_inv_kernel): the lane totals are inverted with the same trick one level up, K2 totals
+//     per Fermat inversion -- one inversion per 32 K K2 / 32 additions instead of one per K.
+//   * pass 2 (msm_ba_p2_kernel): backwards down the rows: 1/d from the running inverse and the stored prefix,
+//     then the addition itself; results to HBM (coalesced, bucket order).
+//   * operands never wait in registers: each lane stages its own points / x's / prefix for the next rows in a
+//     private shared-memory slot ring with cp.async (LDGSTS, 16 B granules, L1 bypass), descriptors (bitmap word,
+//     sorted indices) one and two rows further ahead in registers.  A lane only ever reads its own slot, so no
+//     barrier is needed -- cp.async.wait_group orders a lane's copies before its reads.
+//     Slot stride = odd multiple of 16 B: conflict-free for the 16-byte shared-memory accesses used throughout.
 #pragma once
 #include "msm_acc.cuh"
 
 namespace b2s {
 
-static constexpr int BA_THREADS = 128;
-
 enum : uint32_t { BA_COPY1 = 0, BA_COPY2 = 1, BA_ADD = 2, BA_DBL = 3, BA_INF = 4 };
+enum : uint32_t { BA_F_VALID = 1u, BA_F_SINGLE = 2u };
+
+static constexpr uint32_t BA_KMIN = 16, BA_KMAX = 256;   // rows per unit (chosen on the device from the round's size)
+static constexpr uint32_t BA_K2 = 32;                     // lane totals per Fermat inversion
+static constexpr uint32_t BA_P1_STAGES = 4, BA_P2_STAGES = 2;
+
+__host__ __device__ constexpr uint32_t ba_slot_bytes(uint32_t n) { return ((((n + 15u) / 16u) | 1u)) * 16u; }
 
 template <class F>
-struct BaPair { Affine<F> p1, p2; uint32_t kind; };
+struct BaGeom {
+    static constexpr uint32_t FE = sizeof(F), PT = sizeof(Affine<F>);
+    static constexpr uint32_t P1_META = 2 * FE, P1_SLOT = ba_slot_bytes(2 * FE + 16);
+    static constexpr uint32_t P2_PRE = 2 * PT, P2_META = 2 * PT + FE, P2_SLOT = ba_slot_bytes(2 * PT + FE + 16);
+    // threads per CTA: the G2 slots are twice as big, so half the threads keep three CTAs per SM
+    static constexpr uint32_t THREADS = sizeof(F) > 64 ? 64 : 128;
+    static constexpr uint32_t P1_SMEM = THREADS * BA_P1_STAGES * P1_SLOT, P2_SMEM = THREADS * BA_P2_STAGES * P2_SLOT;
+};
 
-// inputs of output element `o` of bucket g (round input layout in_off, this round's counts via in_off)
-template <class F, bool FIRST>
-__device__ __forceinline__ BaPair<F> ba_load(const Affine<F>* __restrict__ bases, const uint32_t* __restrict__ sorted,
-                                             const Affine<F>* __restrict__ prev, uint32_t in0, bool has2) {
-    BaPair<F> r;
-    if (FIRST) {
-        const uint32_t e1 = sorted[in0];
-        r.p1 = ld_struct(bases + (e1 & 0x7fffffffu));
-        if (e1 >> 31) r.p1.y = r.p1.y.neg();
-        if (has2) {
-            const uint32_t e2 = sorted[in0 + 1];
-            r.p2 = ld_struct(bases + (e2 & 0x7fffffffu));
-            if (e2 >> 31) r.p2.y = r.p2.y.neg();
-        }
-    } else {
-        r.p1 = ld_struct(prev + in0);
-        if (has2) r.p2 = ld_struct(prev + in0 + 1);
-    }
-    if (!has2 || r.p2.is_inf()) r.kind = BA_COPY1;
-    else if (r.p1.is_inf()) r.kind = BA_COPY2;
-    else if (r.p1.x == r.p2.x) r.kind = (r.p1.y == r.p2.y && !r.p1.y.is_zero()) ? BA_DBL : BA_INF;
-    else r.kind = BA_ADD;
+// rows per unit for a round with n_rows rows: enough units to fill the machine, chains as long as that allows
+__host__ __device__ inline uint32_t ba_rows_per_unit(uint32_t n_rows, uint32_t target_units) {
+    uint32_t k = (n_rows + target_units - 1) / target_units;
+    return k < BA_KMIN ? BA_KMIN : (k > BA_KMAX ? BA_KMAX : k);
+}
+
+// ---- cp.async (LDGSTS) ---------------------------------------------------------------------------
+__device__ __forceinline__ void cp_async16(uint32_t smem_addr, const void* gsrc) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr), "l"(gsrc) : "memory");
+}
+template <uint32_t BYTES>
+__device__ __forceinline__ void cp_async_bytes(uint32_t smem_addr, const void* gsrc) {
+    static_assert(BYTES % 16 == 0, "16-byte granules");
+#pragma unroll
+    for (uint32_t i = 0; i < BYTES; i += 16) cp_async16(smem_addr + i, reinterpret_cast<const char*>(gsrc) + i);
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+template <class T>
+__device__ __forceinline__ T lds_struct(uint32_t smem_addr) {
+    static_assert(sizeof(T) % 16 == 0, "16-byte multiples only");
+    T r;
+    uint4* d = reinterpret_cast<uint4*>(&r);
+#pragma unroll
+    for (uint32_t i = 0; i < sizeof(T) / 16; i++)
+        asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(d[i].x), "=r"(d[i].y), "=r"(d[i].z), "=r"(d[i].w) : "r"(smem_addr + 16 * i));
+    return r;
+}
+__device__ __forceinline__ uint4 lds16(uint32_t smem_addr) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(smem_addr));
+    return v;
+}
+__device__ __forceinline__ void sts16(uint32_t smem_addr, uint4 v) {
+    asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(smem_addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
+// coherent vector load (for buffers the same kernel also writes)
+template <class T>
+__device__ __forceinline__ T ld_plain(const T* p) {
+    static_assert(sizeof(T) % 16 == 0, "16-byte multiples only");
+    T r;
+    const uint4* s = reinterpret_cast<const uint4*>(p);
+    uint4* d = reinterpret_cast<uint4*>(&r);
+#pragma unroll
+    for (int i = 0; i < (int)(sizeof(T) / 16); i++) d[i] = s[i];
     return r;
 }
 
+// ---- pair classification (identical in both passes: the denominators must agree) ---------------------
 template <class F>
-__device__ __forceinline__ F ba_denominator(const BaPair<F>& q) {
-    if (q.kind == BA_ADD) return q.p2.x - q.p1.x;
-    if (q.kind == BA_DBL) return q.p1.y.dbl();
+__device__ __forceinline__ uint32_t ba_classify(const Affine<F>& p1, const Affine<F>& p2, bool single) {
+    if (single || p2.is_inf()) return BA_COPY1;
+    if (p1.is_inf()) return BA_COPY2;
+    if (p1.x == p2.x) return (p1.y == p2.y && !p1.y.is_zero()) ? BA_DBL : BA_INF;
+    return BA_ADD;
+}
+template <class F>
+__device__ __forceinline__ F ba_denominator(uint32_t kind, const Affine<F>& p1, const Affine<F>& p2) {
+    if (kind == BA_ADD) return p2.x - p1.x;
+    if (kind == BA_DBL) return p1.y.dbl();
     return F::one();
 }
 
-// Bucket of output `o`: the largest g with off[g] <= o (empty buckets have off[g] == off[g+1] and are skipped).
-// `hint` is a bucket at or before it.  The next bucket is tried first (dense case); otherwise a binary search --
-// never a linear walk: with skewed scalars two non-empty buckets can be 2^19 empty ones apart.
-__device__ __forceinline__ uint32_t ba_bucket_fwd(const uint32_t* __restrict__ off, uint32_t G, uint32_t hint, uint32_t o) {
-    if (off[hint + 1] > o) return hint;
-    if (hint + 2 <= G && off[hint + 2] > o) return hint + 1;
-    uint32_t lo = hint + 1, hi = G;          // off[lo] <= o < off[hi]
-    while (hi - lo > 1) {
-        const uint32_t mid = (lo + hi) >> 1;
-        if (off[mid] <= o) lo = mid; else hi = mid;
-    }
-    return lo;
-}
-// same, searching downwards from a bucket `hint` whose range starts after o
-__device__ __forceinline__ uint32_t ba_bucket_bwd(const uint32_t* __restrict__ off, uint32_t hint, uint32_t o) {
-    if (hint > 0 && off[hint - 1] <= o) return hint - 1;
-    uint32_t lo = 0, hi = hint;              // off[lo] <= o < off[hi]
-    while (hi - lo > 1) {
-        const uint32_t mid = (lo + hi) >> 1;
-        if (off[mid] <= o) lo = mid; else hi = mid;
-    }
-    return lo;
+// descriptor of (row q, this lane): where its inputs are
+struct BaDesc { uint32_t in0, flags; };
+__device__ __forceinline__ BaDesc ba_desc(uint32_t word, uint32_t wr, uint32_t q, uint32_t lane, uint32_t t_out) {
+    const uint32_t o = q * 32u + lane;
+    BaDesc d;
+    d.flags = (o < t_out ? BA_F_VALID : 0u) | (((word >> lane) & 1u) ? BA_F_SINGLE : 0u);
+    d.in0 = 2u * o - (wr + __popc(word & ((1u << lane) - 1u)));
+    return d;
 }
 
-// One thread: outputs [t*K, (t+1)*K) of this round.
+// rare path of pass 1: the pair is not a plain addition (or might not be): fetch the y's and classify exactly
 template <class F, bool FIRST>
-__global__ void __launch_bounds__(BA_THREADS)
-msm_ba_round_kernel(const Affine<F>* __restrict__ bases, const uint32_t* __restrict__ sorted, const Affine<F>* __restrict__ prev,
-                    const uint32_t* __restrict__ in_off, const uint32_t* __restrict__ out_off, uint32_t G, uint32_t K,
-                    F* __restrict__ prefix, Affine<F>* __restrict__ out) {
-    const uint32_t total = out_off[G];
-    const uint64_t o_beg64 = (uint64_t)(blockIdx.x * blockDim.x + threadIdx.x) * K;
-    if (o_beg64 >= total) return;
-    const uint32_t o_beg = (uint32_t)o_beg64;
-    const uint32_t o_end = (uint32_t)min((uint64_t)total, o_beg64 + K);
-    // bucket of the first output: largest g with out_off[g] <= o_beg (skipping empty buckets)
-    uint32_t lo = 0, hi = G;
-    while (hi - lo > 1) {
-        const uint32_t mid = (lo + hi) >> 1;
-        if (out_off[mid] <= o_beg) lo = mid; else hi = mid;
-    }
-    const uint32_t g0 = lo;
-
-    // ---- pass 1: prefix products of the denominators.  Only the x coordinates are needed unless a pair is special
-    // (missing partner, x = 0 which may be the (0,0) encoding of infinity, or equal x): then the y's are fetched and
-    // the pair is classified exactly as pass 2 will.  The next pair's x's are requested before the current
-    // multiplication so that the gather latency hides behind it.
-    F prod = F::one();
-    {
-        uint32_t g = g0, g_out_end = out_off[g + 1], g_in = in_off[g], g_in_end = in_off[g + 1], g_out = out_off[g];
-        struct Xs { F x1, x2; uint32_t in0; bool has2; };
-        auto fetch = [&](uint32_t o) {
-            if (o >= g_out_end) { g = ba_bucket_fwd(out_off, G, g, o); g_out = out_off[g]; g_out_end = out_off[g + 1]; g_in = in_off[g]; g_in_end = in_off[g + 1]; }
-            Xs r;
-            r.in0 = g_in + 2 * (o - g_out);
-            r.has2 = r.in0 + 1 < g_in_end;
-            if (FIRST) {
-                r.x1 = ld_struct(&bases[sorted[r.in0] & 0x7fffffffu].x);
-                r.x2 = r.has2 ? ld_struct(&bases[sorted[r.in0 + 1] & 0x7fffffffu].x) : F::zero();
-            } else {
-                r.x1 = ld_struct(&prev[r.in0].x);
-                r.x2 = r.has2 ? ld_struct(&prev[r.in0 + 1].x) : F::zero();
-            }
-            return r;
-        };
-        Xs nxt = fetch(o_beg);
-        for (uint32_t o = o_beg; o < o_end; o++) {
-            const Xs cur = nxt;
-            if (o + 1 < o_end) nxt = fetch(o + 1);
-            F d;
-            if (cur.has2 && !cur.x1.is_zero() && !cur.x2.is_zero() && cur.x1 != cur.x2) {
-                d = cur.x2 - cur.x1;
-            } else {
-                BaPair<F> q = ba_load<F, FIRST>(bases, sorted, prev, cur.in0, cur.has2);   // rare: full classification
-                d = ba_denominator(q);
-            }
-            st_struct(prefix + o, prod);
-            prod = prod * d;
+__device__ __noinline__ F ba_slow_denominator(const Affine<F>* __restrict__ bases, const Affine<F>* __restrict__ prev, uint32_t e1,
+                                              uint32_t e2, uint32_t in0, bool single) {
+    Affine<F> p1, p2;
+    if (FIRST) {
+        p1 = ld_struct(bases + (e1 & 0x7fffffffu));
+        if (e1 >> 31) p1.y = p1.y.neg();
+        if (!single) {
+            p2 = ld_struct(bases + (e2 & 0x7fffffffu));
+            if (e2 >> 31) p2.y = p2.y.neg();
         }
+    } else {
+        p1 = ld_struct(prev + in0);
+        if (!single) p2 = ld_struct(prev + in0 + 1);
     }
-    F inv = prod.inverse();
-    // ---- pass 2: backwards
-    {
-        // bucket of the last output
-        uint32_t g = ba_bucket_fwd(out_off, G, g0, o_end - 1);
-        uint32_t g_out = out_off[g], g_in = in_off[g], g_in_end = in_off[g + 1];
-        for (uint32_t o = o_end; o-- > o_beg;) {
-            if (o < g_out) { g = ba_bucket_bwd(out_off, g, o); g_out = out_off[g]; g_in = in_off[g]; g_in_end = in_off[g + 1]; }
-            const uint32_t in0 = g_in + 2 * (o - g_out);
-            BaPair<F> q = ba_load<F, FIRST>(bases, sorted, prev, in0, in0 + 1 < g_in_end);
-            const F d = ba_denominator(q);
-            const F dinv = inv * ld_struct(prefix + o);
-            inv = inv * d;
-            Affine<F> res;
-            if (q.kind == BA_ADD || q.kind == BA_DBL) {
-                F num;
-                if (q.kind == BA_ADD) num = q.p2.y - q.p1.y;
-                else { F xx = q.p1.x.sqr(); num = xx.dbl() + xx; }
-                const F lam = num * dinv;
-                const F x3 = lam.sqr() - q.p1.x - q.p2.x;   // DBL: p2 == p1, so this is lambda^2 - 2 x1
-                res.x = x3;
-                res.y = lam * (q.p1.x - x3) - q.p1.y;
-            } else if (q.kind == BA_COPY1) res = q.p1;
-            else if (q.kind == BA_COPY2) res = q.p2;
-            else res = Affine<F>::inf();
-            st_struct(out + o, res);
+    if (single) p2 = Affine<F>::inf();
+    return ba_denominator(ba_classify(p1, p2, single), p1, p2);
+}
+
+// ---- pass 1 -------------------------------------------------------------------------------------------
+// Software pipeline per lane, time step t:  consume row t-S | issue the copies of row t into the slot just freed |
+// descriptor + sorted indices of row t+1 | bitmap word of row t+2.  A row's operands are in flight during the S-1
+// row computations before its own.
+template <class F, bool FIRST>
+__global__ void __launch_bounds__(BaGeom<F>::THREADS)
+msm_ba_p1_kernel(const Affine<F>* __restrict__ bases, const uint32_t* __restrict__ sorted, const Affine<F>* __restrict__ prev,
+                 const uint32_t* __restrict__ bitmap, const uint32_t* __restrict__ wrank, const uint32_t* __restrict__ t_out_p,
+                 uint32_t target_units, F* __restrict__ prefix, F* __restrict__ tot) {
+    using Gm = BaGeom<F>;
+    constexpr uint32_t S = BA_P1_STAGES, FE = Gm::FE;
+    extern __shared__ uint4 ba_smem[];
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const uint32_t smem0 = (uint32_t)__cvta_generic_to_shared(ba_smem) + (warp * S * 32u + lane) * Gm::P1_SLOT;
+    const uint32_t t_out = *t_out_p;
+    const uint32_t n_rows = (t_out + 31u) >> 5;
+    const uint32_t K = ba_rows_per_unit(n_rows, target_units);
+    const uint32_t n_units = (n_rows + K - 1) / K;
+    const uint32_t warps_total = gridDim.x * (blockDim.x >> 5);
+    for (uint32_t u = blockIdx.x * (blockDim.x >> 5) + warp; u < n_units; u += warps_total) {
+        const uint32_t q0 = u * K, nr = min(K, n_rows - q0);
+        F prod = F::one();
+        uint32_t a_word = 0, a_wr = 0;                 // stage A -> B
+        uint32_t b_e1 = 0, b_e2 = 0;                   // stage B -> C
+        BaDesc b_d{0, 0};
+        for (int32_t t = -2; t < (int32_t)(nr + S); t++) {
+            // -- consume row t - S
+            if (t >= (int32_t)S) {
+                cp_async_wait<(int)S - 1>();
+                const uint32_t i = (uint32_t)t - S;
+                const uint32_t slot = smem0 + (i % S) * 32u * Gm::P1_SLOT;
+                const uint4 meta = lds16(slot + Gm::P1_META);   // e1, e2, in0, flags
+                if (meta.w & BA_F_VALID) {
+                    const bool single = (meta.w & BA_F_SINGLE) != 0;
+                    const uint32_t o = (q0 + i) * 32u + lane;
+                    F d = F::one();                              // no partner: the output is a copy
+                    if (!single) {
+                        const F x1 = lds_struct<F>(slot), x2 = lds_struct<F>(slot + FE);
+                        // x = 0 may be the (0,0) encoding of infinity, equal x means doubling or cancellation
+                        if (!x1.is_zero() && !x2.is_zero() && x1 != x2) d = x2 - x1;
+                        else d = ba_slow_denominator<F, FIRST>(bases, prev, meta.x, meta.y, meta.z, false);
+                    }
+                    st_struct(prefix + o, prod);
+                    prod = prod * d;
+                }
+            }
+            // -- issue the copies of row t (descriptor from the previous step); its slot was freed just above
+            if (t >= 0 && (uint32_t)t < nr) {
+                const uint32_t slot = smem0 + ((uint32_t)t % S) * 32u * Gm::P1_SLOT;
+                if (b_d.flags & BA_F_VALID) {
+                    const F* px1 = FIRST ? &bases[b_e1 & 0x7fffffffu].x : &prev[b_d.in0].x;
+                    cp_async_bytes<FE>(slot, px1);
+                    if (!(b_d.flags & BA_F_SINGLE)) {
+                        const F* px2 = FIRST ? &bases[b_e2 & 0x7fffffffu].x : &prev[b_d.in0 + 1].x;
+                        cp_async_bytes<FE>(slot + FE, px2);
+                    }
+                }
+                sts16(slot + Gm::P1_META, make_uint4(b_e1, b_e2, b_d.in0, b_d.flags));
+            }
+            cp_async_commit();
+            // -- descriptor of row t + 1, its sorted indices
+            if (t + 1 >= 0 && (uint32_t)(t + 1) < nr) {
+                b_d = ba_desc(a_word, a_wr, q0 + (uint32_t)(t + 1), lane, t_out);
+                if (FIRST && (b_d.flags & BA_F_VALID)) {
+                    b_e1 = sorted[b_d.in0];
+                    b_e2 = (b_d.flags & BA_F_SINGLE) ? 0u : sorted[b_d.in0 + 1];
+                }
+            }
+            // -- bitmap word of row t + 2
+            if ((uint32_t)(t + 2) < nr) {
+                a_word = bitmap[q0 + (uint32_t)(t + 2)];
+                a_wr = wrank[q0 + (uint32_t)(t + 2)];
+            }
+        }
+        st_struct(tot + (size_t)u * 32u + lane, prod);
+    }
+}
+
+// ---- inversion of the lane totals, in place ------------------------------------------------------------
+template <class F>
+__global__ void __launch_bounds__(128)
+msm_ba_inv_kernel(F* __restrict__ tot, const uint32_t* __restrict__ t_out_p, uint32_t target_units, F* __restrict__ scratch) {
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t t_out = *t_out_p;
+    const uint32_t n_rows = (t_out + 31u) >> 5;
+    const uint32_t K = ba_rows_per_unit(n_rows, target_units);
+    const uint32_t n_tot = ((n_rows + K - 1) / K) * 32u;
+    const uint32_t n_units = (n_tot + 32u * BA_K2 - 1) / (32u * BA_K2);
+    const uint32_t warps_total = gridDim.x * (blockDim.x >> 5);
+    for (uint32_t v = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); v < n_units; v += warps_total) {
+        const uint32_t e0 = v * 32u * BA_K2 + lane;
+        F prod = F::one();
+        for (uint32_t j = 0; j < BA_K2; j++) {
+            const uint32_t e = e0 + 32u * j;
+            if (e < n_tot) {
+                F t = ld_plain(tot + e);
+                st_struct(scratch + e, prod);
+                prod = prod * t;
+            }
+        }
+        F inv = prod.inverse();
+        for (uint32_t j = BA_K2; j-- > 0;) {
+            const uint32_t e = e0 + 32u * j;
+            if (e < n_tot) {
+                F t = ld_plain(tot + e);
+                F p = ld_plain(scratch + e);
+                st_struct(tot + e, inv * p);
+                inv = inv * t;
+            }
         }
     }
 }
 
+// ---- pass 2 -------------------------------------------------------------------------------------------
+// Same pipeline as pass 1, rows in descending order (the running inverse walks the chain backwards).
+template <class F, bool FIRST>
+__global__ void __launch_bounds__(BaGeom<F>::THREADS)
+msm_ba_p2_kernel(const Affine<F>* __restrict__ bases, const uint32_t* __restrict__ sorted, const Affine<F>* __restrict__ prev,
+                 const uint32_t* __restrict__ bitmap, const uint32_t* __restrict__ wrank, const uint32_t* __restrict__ t_out_p,
+                 uint32_t target_units, const F* __restrict__ prefix, const F* __restrict__ tot_inv, Affine<F>* __restrict__ out) {
+    using Gm = BaGeom<F>;
+    constexpr uint32_t S = BA_P2_STAGES, FE = Gm::FE, PT = Gm::PT;
+    extern __shared__ uint4 ba_smem[];
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const uint32_t smem0 = (uint32_t)__cvta_generic_to_shared(ba_smem) + (warp * S * 32u + lane) * Gm::P2_SLOT;
+    const uint32_t t_out = *t_out_p;
+    const uint32_t n_rows = (t_out + 31u) >> 5;
+    const uint32_t K = ba_rows_per_unit(n_rows, target_units);
+    const uint32_t n_units = (n_rows + K - 1) / K;
+    const uint32_t warps_total = gridDim.x * (blockDim.x >> 5);
+    for (uint32_t u = blockIdx.x * (blockDim.x >> 5) + warp; u < n_units; u += warps_total) {
+        const uint32_t q0 = u * K, nr = min(K, n_rows - q0);
+        F inv = ld_struct(tot_inv + (size_t)u * 32u + lane);
+        uint32_t a_word = 0, a_wr = 0, b_e1 = 0, b_e2 = 0;
+        BaDesc b_d{0, 0};
+        // step index i counts rows from the last one down: row q = q0 + nr - 1 - i
+        for (int32_t t = -2; t < (int32_t)(nr + S); t++) {
+            if (t >= (int32_t)S) {
+                cp_async_wait<(int)S - 1>();
+                const uint32_t i = (uint32_t)t - S;
+                const uint32_t slot = smem0 + (i % S) * 32u * Gm::P2_SLOT;
+                const uint4 meta = lds16(slot + Gm::P2_META);   // neg1, neg2, in0, flags
+                if (meta.w & BA_F_VALID) {
+                    const bool single = (meta.w & BA_F_SINGLE) != 0;
+                    const uint32_t o = (q0 + nr - 1 - i) * 32u + lane;
+                    Affine<F> p1 = lds_struct<Affine<F>>(slot), p2;
+                    if (FIRST && meta.x) p1.y = p1.y.neg();
+                    if (!single) {
+                        p2 = lds_struct<Affine<F>>(slot + PT);
+                        if (FIRST && meta.y) p2.y = p2.y.neg();
+                    } else {
+                        p2 = Affine<F>::inf();
+                    }
+                    const uint32_t kind = ba_classify(p1, p2, single);
+                    const F d = ba_denominator(kind, p1, p2);
+                    const F dinv = inv * lds_struct<F>(slot + Gm::P2_PRE);
+                    inv = inv * d;
+                    Affine<F> res;
+                    if (kind == BA_ADD || kind == BA_DBL) {
+                        F num;
+                        if (kind == BA_ADD) num = p2.y - p1.y;
+                        else { F xx = p1.x.sqr(); num = xx.dbl() + xx; }
+                        const F lam = num * dinv;
+                        const F x3 = lam.sqr() - p1.x - p2.x;   // DBL: p2 == p1, so this is lambda^2 - 2 x1
+                        res.x = x3;
+                        res.y = lam * (p1.x - x3) - p1.y;
+                    } else if (kind == BA_COPY1) res = p1;
+                    else if (kind == BA_COPY2) res = p2;
+                    else res = Affine<F>::inf();
+                    st_struct(out + o, res);
+                }
+            }
+            if (t >= 0 && (uint32_t)t < nr) {
+                const uint32_t slot = smem0 + ((uint32_t)t % S) * 32u * Gm::P2_SLOT;
+                if (b_d.flags & BA_F_VALID) {
+                    const uint32_t o = (q0 + nr - 1 - (uint32_t)t) * 32u + lane;
+                    const Affine<F>* a1 = FIRST ? bases + (b_e1 & 0x7fffffffu) : prev + b_d.in0;
+                    cp_async_bytes<PT>(slot, a1);
+                    if (!(b_d.flags & BA_F_SINGLE)) {
+                        const Affine<F>* a2 = FIRST ? bases + (b_e2 & 0x7fffffffu) : prev + b_d.in0 + 1;
+                        cp_async_bytes<PT>(slot + PT, a2);
+                    }
+                    cp_async_bytes<FE>(slot + Gm::P2_PRE, prefix + o);
+                }
+                sts16(slot + Gm::P2_META, make_uint4(b_e1 >> 31, b_e2 >> 31, b_d.in0, b_d.flags));
+            }
+            cp_async_commit();
+            if (t + 1 >= 0 && (uint32_t)(t + 1) < nr) {
+                b_d = ba_desc(a_word, a_wr, q0 + nr - 1 - (uint32_t)(t + 1), lane, t_out);
+                if (FIRST && (b_d.flags & BA_F_VALID)) {
+                    b_e1 = sorted[b_d.in0];
+                    b_e2 = (b_d.flags & BA_F_SINGLE) ? 0u : sorted[b_d.in0 + 1];
+                }
+            }
+            if ((uint32_t)(t + 2) < nr) {
+                a_word = bitmap[q0 + nr - 1 - (uint32_t)(t + 2)];
+                a_wr = wrank[q0 + nr - 1 - (uint32_t)(t + 2)];
+            }
+        }
+    }
+}
+
+// ---- round bookkeeping (tiny kernels, msm.cu) ---------------------------------------------------------
 // counts_next[g] = ceil(counts[g] / 2)
 static __global__ void msm_ba_halve_kernel(const uint32_t* __restrict__ counts, uint32_t G, uint32_t* __restrict__ next) {
     const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
     if (g < G) next[g] = (counts[g] + 1) >> 1;
 }
+// one bit per output of the round: set for the last output of a bucket whose input count is odd
+static __global__ void msm_ba_singles_kernel(const uint32_t* __restrict__ counts_in, const uint32_t* __restrict__ off_out, uint32_t G,
+                                             uint32_t* __restrict__ bitmap) {
+    const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= G) return;
+    const uint32_t c = counts_in[g];
+    if (c & 1u) {
+        const uint32_t last = off_out[g] + ((c + 1u) >> 1) - 1u;
+        atomicOr(&bitmap[last >> 5], 1u << (last & 31u));
+    }
+}
+// wrank[w] = number of set bits in bitmap[0 .. w)   (three kernels: tile sums, spine, apply)
+static constexpr uint32_t BA_SCAN_THREADS = 256, BA_SCAN_PER = 8, BA_SCAN_TILE = BA_SCAN_THREADS * BA_SCAN_PER;
+__device__ __forceinline__ uint32_t ba_block_scan_incl(uint32_t v, uint32_t* total) {
+    __shared__ uint32_t wsum[32];
+    const uint32_t lane = threadIdx.x & 31u, wid = threadIdx.x >> 5;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t o = __shfl_up_sync(0xffffffffu, v, d);
+        if (lane >= (uint32_t)d) v += o;
+    }
+    if (lane == 31) wsum[wid] = v;
+    __syncthreads();
+    const uint32_t nw = (blockDim.x + 31u) >> 5;
+    if (wid == 0) {
+        uint32_t w = lane < nw ? wsum[lane] : 0u;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t o = __shfl_up_sync(0xffffffffu, w, d);
+            if (lane >= (uint32_t)d) w += o;
+        }
+        wsum[lane] = w;
+    }
+    __syncthreads();
+    if (wid > 0) v += wsum[wid - 1];
+    *total = wsum[nw - 1];
+    __syncthreads();
+    return v;
+}
+static __global__ void __launch_bounds__(BA_SCAN_THREADS)
+msm_ba_rank_tiles_kernel(const uint32_t* __restrict__ bitmap, uint32_t n_words, uint32_t* __restrict__ tile_sums) {
+    const uint32_t base = blockIdx.x * BA_SCAN_TILE + threadIdx.x * BA_SCAN_PER;
+    uint32_t v = 0;
+#pragma unroll
+    for (uint32_t k = 0; k < BA_SCAN_PER; k++)
+        if (base + k < n_words) v += __popc(bitmap[base + k]);
+    uint32_t total;
+    ba_block_scan_incl(v, &total);
+    if (threadIdx.x == 0) tile_sums[blockIdx.x] = total;
+}
+static __global__ void __launch_bounds__(1024) msm_ba_rank_spine_kernel(uint32_t* __restrict__ tile_sums, uint32_t n_tiles) {
+    const uint32_t per = (n_tiles + blockDim.x - 1) / blockDim.x;
+    const uint32_t lo = min(threadIdx.x * per, n_tiles), hi = min(lo + per, n_tiles);
+    uint32_t v = 0;
+    for (uint32_t i = lo; i < hi; i++) v += tile_sums[i];
+    uint32_t total;
+    uint32_t run = ba_block_scan_incl(v, &total) - v;
+    for (uint32_t i = lo; i < hi; i++) {
+        const uint32_t t = tile_sums[i];
+        tile_sums[i] = run;
+        run += t;
+    }
+}
+static __global__ void __launch_bounds__(BA_SCAN_THREADS)
+msm_ba_rank_apply_kernel(const uint32_t* __restrict__ bitmap, uint32_t n_words, const uint32_t* __restrict__ tile_sums,
+                         uint32_t* __restrict__ wrank) {
+    const uint32_t base = blockIdx.x * BA_SCAN_TILE + threadIdx.x * BA_SCAN_PER;
+    uint32_t c[BA_SCAN_PER], v = 0;
+#pragma unroll
+    for (uint32_t k = 0; k < BA_SCAN_PER; k++) {
+        c[k] = base + k < n_words ? __popc(bitmap[base + k]) : 0u;
+        v += c[k];
+    }
+    uint32_t total;
+    uint32_t run = tile_sums[blockIdx.x] + ba_block_scan_incl(v, &total) - v;
+#pragma unroll
+    for (uint32_t k = 0; k < BA_SCAN_PER; k++) {
+        if (base + k < n_words) wrank[base + k] = run;
+        run += c[k];
+    }
+}
 
-// implemented in msm_acc_g1.cu / msm_acc_g2.cu (multiplication inlined)
-int32_t msm_ba_round_g1(Ctx* c, bool first, const void* bases, const uint32_t* sorted, const void* prev, const uint32_t* in_off,
-                        const uint32_t* out_off, uint32_t G, uint32_t K, uint64_t out_bound, void* prefix, void* out);
-int32_t msm_ba_round_g2(Ctx* c, bool first, const void* bases, const uint32_t* sorted, const void* prev, const uint32_t* in_off,
-                        const uint32_t* out_off, uint32_t G, uint32_t K, uint64_t out_bound, void* prefix, void* out);
+// One round's three arithmetic kernels; implemented in msm_acc_g1.cu / msm_acc_g2.cu (multiplication inlined).
+struct BaRoundArgs {
+    bool first;
+    const void* bases;            // first round: the MSM's bases, gathered through `sorted`
+    const uint32_t* sorted;
+    const void* prev;             // later rounds: the previous round's output (bucket order)
+    const uint32_t* bitmap;
+    const uint32_t* wrank;
+    const uint32_t* t_out;        // device: number of outputs of this round
+    uint32_t target_units;
+    void* prefix;                 // F[t_out bound]
+    void* tot;                    // F[lane totals bound]
+    void* inv_scratch;            // F[lane totals bound]
+    void* out;                    // Affine<F>[t_out bound]
+};
+int32_t msm_ba_round_g1(Ctx* c, const BaRoundArgs& a);
+int32_t msm_ba_round_g2(Ctx* c, const BaRoundArgs& a);
 
 template <class F>
-static int32_t msm_ba_round_launch(Ctx* c, const char* label, bool first, const void* bases, const uint32_t* sorted, const void* prev,
-                                   const uint32_t* in_off, const uint32_t* out_off, uint32_t G, uint32_t K, uint64_t out_bound,
-                                   void* prefix, void* out) {
-    const unsigned grid = cdiv(cdiv(out_bound, K), BA_THREADS);
-    if (grid == 0) return B2S_OK;
-    if (first)
-        B2S_LAUNCH_N(c, label, (msm_ba_round_kernel<F, true>), grid, BA_THREADS, 0, reinterpret_cast<const Affine<F>*>(bases), sorted,
-                     reinterpret_cast<const Affine<F>*>(prev), in_off, out_off, G, K, reinterpret_cast<F*>(prefix),
-                     reinterpret_cast<Affine<F>*>(out));
+static int32_t msm_ba_round_launch(Ctx* c, const char* l1, const char* li, const char* l2, const BaRoundArgs& a) {
+    using Gm = BaGeom<F>;
+    const Affine<F>* bases = reinterpret_cast<const Affine<F>*>(a.bases);
+    const Affine<F>* prev = reinterpret_cast<const Affine<F>*>(a.prev);
+    F* prefix = reinterpret_cast<F*>(a.prefix);
+    F* tot = reinterpret_cast<F*>(a.tot);
+    // persistent grids: as many CTAs as fit (shared-memory bound), units are handed out round-robin
+    const unsigned ctas1 = (unsigned)c->sm_count * max(1u, (220u * 1024u) / (Gm::P1_SMEM + 1024u));
+    const unsigned ctas2 = (unsigned)c->sm_count * max(1u, (220u * 1024u) / (Gm::P2_SMEM + 1024u));
+    if (a.first) {
+        B2S_CUDA(c, cudaFuncSetAttribute(msm_ba_p1_kernel<F, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Gm::P1_SMEM));
+        B2S_CUDA(c, cudaFuncSetAttribute(msm_ba_p2_kernel<F, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Gm::P2_SMEM));
+        B2S_LAUNCH_N(c, l1, (msm_ba_p1_kernel<F, true>), ctas1, Gm::THREADS, Gm::P1_SMEM, bases, a.sorted, prev, a.bitmap, a.wrank, a.t_out,
+                     a.target_units, prefix, tot);
+    } else {
+        B2S_CUDA(c, cudaFuncSetAttribute(msm_ba_p1_kernel<F, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Gm::P1_SMEM));
+        B2S_CUDA(c, cudaFuncSetAttribute(msm_ba_p2_kernel<F, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Gm::P2_SMEM));
+        B2S_LAUNCH_N(c, l1, (msm_ba_p1_kernel<F, false>), ctas1, Gm::THREADS, Gm::P1_SMEM, bases, a.sorted, prev, a.bitmap, a.wrank, a.t_out,
+                     a.target_units, prefix, tot);
+    }
+    B2S_LAUNCH_N(c, li, msm_ba_inv_kernel<F>, 4 * c->sm_count, 128, 0, tot, a.t_out, a.target_units, reinterpret_cast<F*>(a.inv_scratch));
+    if (a.first)
+        B2S_LAUNCH_N(c, l2, (msm_ba_p2_kernel<F, true>), ctas2, Gm::THREADS, Gm::P2_SMEM, bases, a.sorted, prev, a.bitmap, a.wrank, a.t_out,
+                     a.target_units, (const F*)prefix, (const F*)tot, reinterpret_cast<Affine<F>*>(a.out));
     else
-        B2S_LAUNCH_N(c, label, (msm_ba_round_kernel<F, false>), grid, BA_THREADS, 0, reinterpret_cast<const Affine<F>*>(bases), sorted,
-                     reinterpret_cast<const Affine<F>*>(prev), in_off, out_off, G, K, reinterpret_cast<F*>(prefix),
-                     reinterpret_cast<Affine<F>*>(out));
+        B2S_LAUNCH_N(c, l2, (msm_ba_p2_kernel<F, false>), ctas2, Gm::THREADS, Gm::P2_SMEM, bases, a.sorted, prev, a.bitmap, a.wrank, a.t_out,
+                     a.target_units, (const F*)prefix, (const F*)tot, reinterpret_cast<Affine<F>*>(a.out));
     return B2S_OK;
 }
 

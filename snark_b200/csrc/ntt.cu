@@ -272,14 +272,10 @@ static int32_t ntt_run_t(Ctx* c, void* data_dev, uint32_t log_n, bool inverse, b
     const PowTab post = (inverse && coset) ? pl->coset_out_scaled : none;
     const void* post_const = (inverse && !coset) ? pl->n_inv : nullptr;
 
-    static bool attr_set[2] = {false, false};
     const size_t smem_bytes = ((size_t)(1u << NTT_TILE_LOG) * 2 + (1u << NTT_MAX_RADIX_LOG) + 2) * sizeof(uint4) +
                               (size_t)(1u << (NTT_MAX_RADIX_LOG - 1)) * sizeof(Fr);
-    if (!attr_set[Curve::id]) {
-        B2S_CUDA(c, cudaFuncSetAttribute(ntt_pass_strided<Fr>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
-        B2S_CUDA(c, cudaFuncSetAttribute(ntt_pass_final<Fr>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
-        attr_set[Curve::id] = true;
-    }
+    B2S_SMEM_ATTR(c, ntt_pass_strided<Fr>, smem_bytes);
+    B2S_SMEM_ATTR(c, ntt_pass_final<Fr>, smem_bytes);
 
     uint32_t log_p = 0;
     const Fr* src = data;

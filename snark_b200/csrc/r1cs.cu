@@ -156,10 +156,12 @@ static int32_t r1cs_upload_t(Ctx* c, uint64_t n_rows, uint64_t n_instance, uint6
         if ((st = m->row_ptr[k].alloc(c, (n_rows + 1) * 8)) != B2S_OK) break;
         if ((st = m->col[k].alloc(c, nnz * 4)) != B2S_OK) break;
         if ((st = m->coeff_id[k].alloc(c, nnz * 4)) != B2S_OK) break;
-        cudaMemcpyAsync(m->row_ptr[k].p, row_ptr[k], (n_rows + 1) * 8, cudaMemcpyHostToDevice, c->stream);
-        if (nnz) cudaMemcpyAsync(m->col[k].p, col[k], nnz * 4, cudaMemcpyHostToDevice, c->stream);
-        if (nnz) cudaMemcpyAsync(m->coeff_id[k].p, cid.data(), nnz * 4, cudaMemcpyHostToDevice, c->stream);
-        cudaStreamSynchronize(c->stream);  // cid goes out of scope
+        cudaError_t ce = cudaMemcpyAsync(m->row_ptr[k].p, row_ptr[k], (n_rows + 1) * 8, cudaMemcpyHostToDevice, c->stream);
+        if (ce == cudaSuccess && nnz) ce = cudaMemcpyAsync(m->col[k].p, col[k], nnz * 4, cudaMemcpyHostToDevice, c->stream);
+        if (ce == cudaSuccess && nnz) ce = cudaMemcpyAsync(m->coeff_id[k].p, cid.data(), nnz * 4, cudaMemcpyHostToDevice, c->stream);
+        const cudaError_t se = cudaStreamSynchronize(c->stream);  // cid goes out of scope
+        if (ce == cudaSuccess) ce = se;
+        if (ce != cudaSuccess) { st = fail(c, B2S_ERR_CUDA, "r1cs upload of matrix %d failed: %s", k, cudaGetErrorString(ce)); break; }
     }
     if (st == B2S_OK) {
         m->pool_size = (uint32_t)pool.size();

@@ -116,6 +116,7 @@ static int32_t setup_t(Ctx* c, const b2s_r1cs* m, const void* trapdoor_host, b2s
         return fail(c, B2S_ERR_INVALID_ARG, "setup: more than 2^32 variables or nonzeros");
     // host: a handful of field operations on the trapdoor (constants of the kernels)
     SetupConsts<Fr> k;
+    HostWipe wipe_k{&k, sizeof(k)};   // the trapdoor copy on this stack frame does not outlive the call
     const Fr* td = reinterpret_cast<const Fr*>(trapdoor_host);
     k.tau = td[0]; k.alpha = td[1]; k.beta = td[2]; k.gamma = td[3]; k.delta = td[4];
     if (k.gamma.is_zero() || k.delta.is_zero()) return fail(c, B2S_ERR_DIVISION_BY_ZERO, "setup: gamma or delta is zero");
@@ -132,6 +133,7 @@ static int32_t setup_t(Ctx* c, const b2s_r1cs* m, const void* trapdoor_host, b2s
     k.zt_over_n = zt * n_inv; k.zt_dinv = zt * k.dinv;
 
     DevBuf u, abc3, lq, gabc, hq;
+    u.secret = abc3.secret = lq.secret = gabc.secret = hq.secret = true;   // powers of tau, delta^-1, ...
     B2S_TRY(u.alloc(c, N * sizeof(Fr)));
     B2S_LAUNCH(c, lagrange_kernel<Fr>, cdiv(N, 128), 128, 0, k, N, u.as<Fr>());
     B2S_TRY(abc3.alloc(c, 3 * n_vars * sizeof(Fr)));
@@ -168,6 +170,7 @@ static int32_t setup_t(Ctx* c, const b2s_r1cs* m, const void* trapdoor_host, b2s
     // group part
     const size_t g1 = sizeof(typename Curve::G1Affine), g2 = sizeof(typename Curve::G2Affine);
     DevBuf qa, qb1, qb2, qh, ql, qabc, k1, k2, ks;
+    ks.secret = true;
     B2S_TRY(qa.alloc(c, n_vars * g1)); B2S_TRY(qb1.alloc(c, n_vars * g1)); B2S_TRY(qb2.alloc(c, n_vars * g2));
     B2S_TRY(qh.alloc(c, N * g1)); B2S_TRY(ql.alloc(c, (mw + 1) * g1)); B2S_TRY(qabc.alloc(c, ell * g1));
     B2S_TRY(fixed_base_run(c, 1, a, n_vars, true, qa.p));

@@ -70,7 +70,16 @@ def test_ntt_round_trip_large(be, log_n):
     be.ntt(y, log_n)
     be.sync()
     assert not torch.equal(x, y)
-    # the first 2^12-point sub-problem: X[k * n/4096] = NTT_4096 of the length-4096 folding of x
+    # the first 2^12-point sub-problem against the oracle: X[k * n/4096], k < 4096, is the
+    # 4096-point NTT of x folded to length 4096 (y[j] = sum_m x[j + 4096 m]) -- 4096 outputs, each a sum over all inputs
+    from tests.util import limbs_to_ints
+
+    sub = 4096
+    Rinv = pow(1 << 256, -1, curve.r)
+    xs = limbs_to_ints(raw)
+    folded = [sum(xs[j::sub]) * Rinv % curve.r for j in range(sub)]
+    got_sub = y.view(n, 8)[:: n // sub].contiguous().cpu().numpy().view(np.uint32).reshape(-1)
+    assert unpack_fr(curve, got_sub) == ontt.ntt(curve, folded)
     be.ntt(y, log_n, inverse=True)
     be.sync()
     assert torch.equal(x, y)
@@ -81,11 +90,6 @@ def test_ntt_round_trip_large(be, log_n):
     # linearity spot-check against the oracle: NTT(x)[0] = sum x, NTT(x)[n/2] = sum (-1)^j x_j
     be.ntt(y, log_n)
     be.sync()
-    curve = CURVES[be.curve]
-    from tests.util import limbs_to_ints
-
-    Rinv = pow(1 << 256, -1, curve.r)
-    xs = limbs_to_ints(raw)
     s0 = sum(xs) * Rinv % curve.r
     s1 = (sum(xs[0::2]) - sum(xs[1::2])) * Rinv % curve.r
     got = y.cpu().numpy().view(np.uint32)

@@ -2,6 +2,7 @@
 oracle, which is itself pinned by the definitions in tests/test_oracle_py.py."""
 import random
 
+import numpy as np
 import pytest
 
 from oracle import cnative
@@ -70,6 +71,7 @@ def test_c_groth16(cid):
     a, b, c, hh = cnative.groth16_prove(cid, csr, len(mats[0]), len(inst), len(wit), arrays, pack_fr(curve, inst),
                                         pack_fr(curve, wit), pack_fr(curve, [rr]), pack_fr(curve, [ss]), want_h=True, threads=4)
     assert unpack_fr(curve, hh) == h
+    assert np.array_equal(cnative.witness_map(cid, csr, len(mats[0]), len(inst), pack_fr(curve, z), threads=3), hh)   # stand-alone export
     assert (unpack_points(curve, 1, a)[0], unpack_points(curve, 2, b)[0], unpack_points(curve, 1, c)[0]) == (A, B, C)
     x = [rng.randrange(curve.r) for _ in range(50)]
     y = [rng.randrange(curve.r) for _ in range(50)]

@@ -1,11 +1,8 @@
 """SURVEY 8(f) row 1 on the device: b2s_r1cs_upload_lcmap must give the same handle as b2s_r1cs_upload fed with
 to_matrices() -- same SpMV, same proof.
 
-The entry point was written when this round's GPU budget was almost spent.  What has been seen green on a B200 is
-exactly `test_lcmap_spmv_equals_matrix_path` (tools/lcmap_probe.py, profiles/r01_gpu_lcmap_probe.txt: both curves, five
-circuits); the remaining tests (setup + prove from the LcMap handle, the error path, the C++ host) exercise code whose
-per-row logic is verified on the host (tests/test_host_lcmap.py) but which has not run on a device yet, so they stay
-opt-in (B2S_RUN_UNVALIDATED=1) until they have."""
+All of it has run green on a B200 (profiles/r02_gpu_job1.txt): the handle, setup + prove from it, the error path and the
+C++ host through B2S_HOST_LCMAP=1."""
 import os
 import random
 
@@ -19,7 +16,6 @@ from tests.test_host_lcmap import circuits
 from tests.util import csr_from_rows, pack_fr, unpack_fr, unpack_points
 
 pytestmark = pytest.mark.gpu
-unvalidated = pytest.mark.skipif(os.environ.get("B2S_RUN_UNVALIDATED") != "1", reason="not yet run on a B200 (opt in with B2S_RUN_UNVALIDATED=1)")
 CURVES = [BLS12_381, BN254]
 
 
@@ -56,7 +52,6 @@ def test_lcmap_spmv_equals_matrix_path(be):
         be.r1cs_free(m_ref); be.r1cs_free(m_lc)
 
 
-@unvalidated
 def test_lcmap_handle_equals_matrix_handle(be):
     curve = CURVES[be.curve]
     rng = random.Random(0xB2000005)
@@ -83,7 +78,6 @@ def test_lcmap_handle_equals_matrix_handle(be):
         be.r1cs_free(m_ref); be.r1cs_free(m_lc)
 
 
-@unvalidated
 def test_lcmap_errors(be):
     from snark_b200.lib import B2SError
 
@@ -94,7 +88,6 @@ def test_lcmap_errors(be):
     assert e.value.code == 16 and "finalize" in str(e.value)
 
 
-@unvalidated
 @pytest.mark.parametrize("cid,circuit", [(0, "circuit2"), (1, "dummy")])
 def test_cpp_host_proves_through_the_lcmap_path(cid, circuit):
     """The C++ mirror hands its flat LcMap to b2s_r1cs_upload_lcmap (B2S_HOST_LCMAP=1): same proof as the oracle's."""

@@ -33,5 +33,7 @@ for group in groups:
             print(f"G{group} 2^{log_n} rounds={r} K={k} {name:8s} {e0.elapsed_time(e1)/2:8.2f} ms  same_result={ok}", flush=True)
             if os.environ.get("PROBE_PROFILE"):
                 be.profile(True); fn(bases, s, n); rep = be.profile_report(); be.profile(False)
-                print("    " + ", ".join(f"{k.split('<')[0]}={v[1]:.2f}" for k, v in sorted(rep.items(), key=lambda kv: -kv[1][1])[:9]), flush=True)
+                top = int(os.environ.get("PROBE_TOP", "9"))
+                print(f"    kernel sum {sum(v[1] for v in rep.values()):.2f} ms in {sum(v[0] for v in rep.values())} launches: " +
+                      ", ".join(f"{k.split('<')[0]}={v[1]:.2f}" for k, v in sorted(rep.items(), key=lambda kv: -kv[1][1])[:top]), flush=True)
     del bases
