@@ -64,6 +64,7 @@ extern "C" {
 #define B2S_ERR_NO_DEVICE 17
 #define B2S_ERR_CUDA 18
 #define B2S_ERR_OOM 19
+#define B2S_ERR_NCCL 20
 
 typedef struct b2s_ctx b2s_ctx;
 typedef struct b2s_r1cs b2s_r1cs;   /* device-resident A/B/C in CSR (witness independent; upload once per circuit) */
@@ -137,6 +138,11 @@ int32_t b2s_spmv(b2s_ctx* ctx, const b2s_r1cs* m, const void* z, int32_t mem, vo
  * out_h receives domain_size elements (the top one is 0); domain_size = next_pow2(n_rows + n_instance). */
 int32_t b2s_witness_map(b2s_ctx* ctx, const b2s_r1cs* m, const void* z, int32_t mem, void* out_h);
 uint64_t b2s_r1cs_domain_size(const b2s_r1cs* m);
+/* The same h computed by the DISTRIBUTED schedule of b2s_groth16_prove_group (four-step transforms, SpMV and quotient on
+ * column slabs) with 2^log_ranks virtual ranks on this one GPU, the all-to-all replaced by device copies.
+ * Exists so that the index algebra of the multi-GPU path is checked bit for bit on a one-GPU box; B2S_ERR_INVALID_ARG
+ * when the domain cannot be cut that way (log2(domain) odd, or too few rows per rank). */
+int32_t b2s_witness_map_sim(b2s_ctx* ctx, const b2s_r1cs* m, const void* z, int32_t mem, uint32_t log_ranks, void* out_h);
 
 /* ---- Groth16 (ark-groth16 ProvingKey / create_proof_with_reduction) ------------
  * Query vectors are affine point arrays in HOST or DEVICE memory (`mem`); they are copied to the GPU.
@@ -191,6 +197,27 @@ int32_t b2s_groth16_prove_shard_resident(b2s_ctx* ctx, const b2s_pk* pk, const b
 int32_t b2s_groth16_finish(b2s_ctx* ctx, const b2s_pk* pk, const void* g1_partials, const void* g2_partials,
                            uint32_t n_shards, const void* r, const void* s, void* out_a_g1, void* out_b_g2,
                            void* out_c_g1);
+
+/* ---- multi-GPU group (SURVEY 8(b) `b2s_ctx_create(curve, n_gpus)` / 8(e)): one rank per GPU, NCCL inside -------------
+ * So that ONE `SNARK::prove` (snark/src/lib.rs:50-54) drives every GPU of a box: each rank (process, or host thread with
+ * its own ctx) holds a base-range SHARD of the proving key (b2s_pk_upload with offsets), the same matrices and the same z;
+ * the call computes the rank's five MSM partial sums, all-gathers them with NCCL on the ctx stream (device buffers, 1.2 KiB
+ * per rank -- EC addition is not an NCCL reduction) and rank 0 joins them and applies the r/s epilogue.
+ * NCCL (libnccl.so.2) is bound at run time; B2S_ERR_NCCL if it is missing or fails.  world == 1 needs no NCCL.
+ *   b2s_group_unique_id   rank 0 draws the NCCL id (128 bytes) and hands it to the other ranks by the host program's
+ *                         own channel (torch.distributed / MPI / a file);
+ *   b2s_group_create      collective over all ranks;
+ *   b2s_groth16_prove_group[_resident]   collective; the proof is written on rank 0 (outputs may be NULL elsewhere). */
+typedef struct b2s_group b2s_group;
+#define B2S_GROUP_ID_BYTES 128
+int32_t b2s_group_unique_id(uint8_t out[B2S_GROUP_ID_BYTES]);
+int32_t b2s_group_create(b2s_ctx* ctx, const uint8_t id[B2S_GROUP_ID_BYTES], int32_t rank, int32_t world, b2s_group** out);
+void b2s_group_destroy(b2s_group* group);
+int32_t b2s_groth16_prove_group(b2s_group* group, const b2s_pk* pk_shard, const b2s_r1cs* m, const void* z_instance,
+                                const void* z_witness, const void* r, const void* s, void* out_a_g1, void* out_b_g2,
+                                void* out_c_g1);
+int32_t b2s_groth16_prove_group_resident(b2s_group* group, const b2s_pk* pk_shard, const b2s_r1cs* m, const void* z_dev,
+                                         const void* r, const void* s, void* out_a_g1, void* out_b_g2, void* out_c_g1);
 
 /* ---- wire format: CanonicalSerialize::serialize_compressed of group elements / Proof --------
  * (snark/src/lib.rs:25-36 bounds).  BLS12-381: zcash/IETF big-endian form, 48 B (G1) / 96 B (G2); BN254: ark-ec

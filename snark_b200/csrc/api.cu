@@ -5,6 +5,7 @@
 #include <cstring>
 
 #include "common.cuh"
+#include "dntt.cuh"
 #include "r1cs.cuh"
 
 using namespace b2s;
@@ -306,6 +307,24 @@ int32_t b2s_witness_map(b2s_ctx* ctx, const b2s_r1cs* m, const void* z, int32_t 
     DevBuf h;
     B2S_TRY(h.alloc(ctx, nh));
     B2S_TRY(witness_map_run(ctx, m, zi.dptr, h.p));
+    B2S_CUDA(ctx, cudaMemcpyAsync(out_h, h.p, nh, cudaMemcpyDeviceToHost, ctx->stream));
+    B2S_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return B2S_OK;
+}
+
+int32_t b2s_witness_map_sim(b2s_ctx* ctx, const b2s_r1cs* m, const void* z, int32_t mem, uint32_t log_ranks, void* out_h) {
+    LOCK(ctx);
+    if (!m) return fail(ctx, B2S_ERR_MISSING_CS, "witness_map_sim: null matrices");
+    if (!z || !out_h) return fail(ctx, B2S_ERR_INVALID_ARG, "witness_map_sim: null buffer");
+    if (!dist_supported(m->log_domain, log_ranks))
+        return fail(ctx, B2S_ERR_INVALID_ARG, "witness_map_sim: domain 2^%u cannot be cut over 2^%u ranks", m->log_domain, log_ranks);
+    const size_t nz = (m->n_instance + m->n_witness) * 32, nh = (size_t)32 << m->log_domain;
+    if (mem == B2S_MEM_DEVICE) return witness_map_sim(ctx, m, z, log_ranks, out_h);
+    InBuf zi;
+    B2S_TRY(zi.bind(ctx, z, nz, mem));
+    DevBuf h;
+    B2S_TRY(h.alloc(ctx, nh));
+    B2S_TRY(witness_map_sim(ctx, m, zi.dptr, log_ranks, h.p));
     B2S_CUDA(ctx, cudaMemcpyAsync(out_h, h.p, nh, cudaMemcpyDeviceToHost, ctx->stream));
     B2S_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return B2S_OK;

@@ -72,11 +72,11 @@ __global__ void groth16_epilogue_g2_kernel(const Affine<typename Curve::Fq2>* co
     *out_b = acc.to_affine();
 }
 
-// sums[j] = sum over shards of partials[shard * stride + j]
+// sums[j] = sum over shards of partials[shard * stride + j], j < count
 template <class F>
-__global__ void sum_shards_kernel(const XYZZ<F>* partials, uint32_t n_shards, uint32_t stride, XYZZ<F>* sums) {
+__global__ void sum_shards_kernel(const XYZZ<F>* partials, uint32_t n_shards, uint32_t stride, uint32_t count, XYZZ<F>* sums) {
     const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= stride) return;
+    if (j >= count) return;
     XYZZ<F> acc = XYZZ<F>::identity();
     for (uint32_t sidx = 0; sidx < n_shards; sidx++) acc.add(partials[sidx * stride + j]);
     sums[j] = acc;
@@ -138,9 +138,20 @@ int32_t pk_upload(Ctx* c, const b2s_pk_desc* d, int32_t mem, b2s_pk** out) {
     return B2S_OK;
 }
 
+// the whole h on this GPU
+struct ReplicatedH : HSource {
+    DevBuf h;
+    int32_t get(Ctx* c, const b2s_pk* pk, const b2s_r1cs* m, const void* z_dev, const void** h_for_shard) override {
+        B2S_TRY(h.alloc(c, (size_t)32 << m->log_domain));
+        B2S_TRY(witness_map_run(c, m, z_dev, h.p));
+        *h_for_shard = h.as<char>() + pk->h_off * 32;
+        return B2S_OK;
+    }
+};
+
 template <class Curve>
 static int32_t shard_t(Ctx* c, const b2s_pk* pk, const b2s_r1cs* m, const void* z_inst, const void* z_wit, const void* z_dev,
-                       const void* r_host, const void* s_host, void* g1_out, void* g2_out) {
+                       const void* r_host, const void* s_host, void* g1_out, void* g2_out, HSource* hs) {
     using Fr = typename Curve::Fr;
     using P1 = XYZZ<typename Curve::Fq>;
     using P2 = XYZZ<typename Curve::Fq2>;
@@ -151,9 +162,10 @@ static int32_t shard_t(Ctx* c, const b2s_pk* pk, const b2s_r1cs* m, const void* 
                     (unsigned long long)m->n_instance, (unsigned long long)m->n_witness, (unsigned long long)N);
     const uint64_t n_vars = m->n_instance + m->n_witness;
     // z_ext = z ++ [r, s]
-    DevBuf z, h, tails;
+    DevBuf z, tails;
+    ReplicatedH replicated;
+    if (!hs) hs = &replicated;
     B2S_TRY(z.alloc(c, (n_vars + 2) * sizeof(Fr)));
-    B2S_TRY(h.alloc(c, N * sizeof(Fr)));
     B2S_TRY(tails.alloc(c, 4 * 64 * sizeof(P1) + 64 * sizeof(P2)));
     // Horner tails run on c->aux and read `tails` / write the outputs: whatever way this function is left, the aux
     // stream must be done before the buffers above (and the caller's outputs) go back to the pool
@@ -185,22 +197,24 @@ static int32_t shard_t(Ctx* c, const b2s_pk* pk, const b2s_r1cs* m, const void* 
     B2S_TRY(msm_run(c, 1, pk->a_query.p, zd + pk->a_off, pk->a_len + pk->a_ext, true, g1 + 2, w1 + 2 * 64));
     B2S_TRY(msm_run(c, 1, pk->b_g1_query.p, zd + pk->b1_off, pk->b1_len + pk->b1_ext, true, g1 + 3, w1 + 3 * 64));
     B2S_TRY(msm_run(c, 1, pk->l_query.p, zd + m->n_instance + pk->l_off, pk->l_len, true, g1 + 1, w1 + 1 * 64));
-    B2S_TRY(witness_map_run(c, m, zd, h.p));
-    B2S_TRY(msm_run(c, 1, pk->h_query.p, h.as<Fr>() + pk->h_off, pk->h_len, true, g1 + 0, w1 + 0 * 64));
+    const void* h_shard = nullptr;
+    B2S_TRY(hs->get(c, pk, m, zd, &h_shard));
+    B2S_TRY(msm_run(c, 1, pk->h_query.p, h_shard, pk->h_len, true, g1 + 0, w1 + 0 * 64));
     B2S_TRY(msm_join_tails(c));
     return B2S_OK;
 }
 
 int32_t groth16_shard(Ctx* c, const b2s_pk* pk, const b2s_r1cs* m, const void* z_inst, const void* z_wit, const void* z_dev,
-                      const void* r_host, const void* s_host, void* g1_out, void* g2_out) {
+                      const void* r_host, const void* s_host, void* g1_out, void* g2_out, HSource* hs) {
     return dispatch_curve(c, [&](auto curve) {
-        return shard_t<decltype(curve)>(c, pk, m, z_inst, z_wit, z_dev, r_host, s_host, g1_out, g2_out);
+        return shard_t<decltype(curve)>(c, pk, m, z_inst, z_wit, z_dev, r_host, s_host, g1_out, g2_out, hs);
     });
 }
 
+// g1_partials: shard i's four G1 sums start at element i * g1_stride (XYZZ<Fq> units); g2_partials likewise (XYZZ<Fq2>)
 template <class Curve>
-static int32_t finish_t(Ctx* c, const b2s_pk* pk, const void* g1_partials, const void* g2_partials, uint32_t n_shards,
-                        const void* r_host, const void* s_host, void* out_a, void* out_b, void* out_c) {
+static int32_t finish_t(Ctx* c, const b2s_pk* pk, const void* g1_partials, uint32_t g1_stride, const void* g2_partials, uint32_t g2_stride,
+                        uint32_t n_shards, const void* r_host, const void* s_host, void* out_a, void* out_b, void* out_c) {
     using Fr = typename Curve::Fr;
     using Fq = typename Curve::Fq;
     using Fq2 = typename Curve::Fq2;
@@ -210,8 +224,8 @@ static int32_t finish_t(Ctx* c, const b2s_pk* pk, const void* g1_partials, const
     B2S_CUDA(c, cudaMemcpyAsync(rs.as<Fr>() + 1, s_host, sizeof(Fr), cudaMemcpyHostToDevice, c->stream));
     B2S_TRY(sums1.alloc(c, 4 * sizeof(XYZZ<Fq>)));
     B2S_TRY(sums2.alloc(c, sizeof(XYZZ<Fq2>)));
-    B2S_LAUNCH(c, sum_shards_kernel<Fq>, 1, 32, 0, reinterpret_cast<const XYZZ<Fq>*>(g1_partials), n_shards, 4u, sums1.as<XYZZ<Fq>>());
-    B2S_LAUNCH(c, sum_shards_kernel<Fq2>, 1, 32, 0, reinterpret_cast<const XYZZ<Fq2>*>(g2_partials), n_shards, 1u, sums2.as<XYZZ<Fq2>>());
+    B2S_LAUNCH(c, sum_shards_kernel<Fq>, 1, 32, 0, reinterpret_cast<const XYZZ<Fq>*>(g1_partials), n_shards, g1_stride, 4u, sums1.as<XYZZ<Fq>>());
+    B2S_LAUNCH(c, sum_shards_kernel<Fq2>, 1, 32, 0, reinterpret_cast<const XYZZ<Fq2>*>(g2_partials), n_shards, g2_stride, 1u, sums2.as<XYZZ<Fq2>>());
     const size_t g1 = sizeof(Affine<Fq>), g2 = sizeof(Affine<Fq2>);
     B2S_TRY(outs.alloc(c, 2 * g1 + g2));
     char* o = outs.as<char>();
@@ -229,7 +243,19 @@ static int32_t finish_t(Ctx* c, const b2s_pk* pk, const void* g1_partials, const
 int32_t groth16_finish(Ctx* c, const b2s_pk* pk, const void* g1_partials_dev, const void* g2_partials_dev, uint32_t n_shards,
                        const void* r_host, const void* s_host, void* out_a, void* out_b, void* out_c) {
     return dispatch_curve(c, [&](auto curve) {
-        return finish_t<decltype(curve)>(c, pk, g1_partials_dev, g2_partials_dev, n_shards, r_host, s_host, out_a, out_b, out_c);
+        return finish_t<decltype(curve)>(c, pk, g1_partials_dev, 4u, g2_partials_dev, 1u, n_shards, r_host, s_host, out_a, out_b, out_c);
+    });
+}
+
+// The all-gathered layout of group.cu: rank i's packet = [4 G1 XYZZ | 1 G2 XYZZ] at byte i * (4 |P1| + |P2|); |P2| = 2 |P1|,
+// so the G1 sums sit at stride 6 (P1 units) and the G2 sum at element 2 + 3 i (P2 units).
+int32_t groth16_finish_strided(Ctx* c, const b2s_pk* pk, const void* packed_dev, uint32_t n_shards, const void* r_host, const void* s_host,
+                               void* out_a, void* out_b, void* out_c) {
+    return dispatch_curve(c, [&](auto curve) {
+        using C = decltype(curve);
+        static_assert(sizeof(XYZZ<typename C::Fq2>) == 2 * sizeof(XYZZ<typename C::Fq>), "packet layout");
+        const char* base = reinterpret_cast<const char*>(packed_dev);
+        return finish_t<C>(c, pk, base, 6u, base + 4 * sizeof(XYZZ<typename C::Fq>), 3u, n_shards, r_host, s_host, out_a, out_b, out_c);
     });
 }
 

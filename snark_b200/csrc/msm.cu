@@ -28,6 +28,8 @@
 // Roofline: per (point, scalar) the algorithmic HBM traffic is 96+32 B (G1 BLS12-381), but each point
 // costs ceil(255/c) mixed additions of ~10 Fq multiplications = ~3000 wide IMADs; the kernel is
 // bound by the fma pipe by two orders of magnitude over HBM (DESIGN.md has the numbers).
+#include <algorithm>
+
 #include "msm_affine.cuh"
 
 namespace b2s {
@@ -440,8 +442,42 @@ static int32_t msm_run_t(Ctx* c, const void* bases_dev, const void* scalars_dev,
         B2S_CUDA(c, cudaMemsetAsync(out, 0, sizeof(Pt), c->stream));
         return B2S_OK;
     }
-    const MsmShape sh = msm_shape(n, Curve::FrP::BITS, sizeof(Pt));
+    MsmShape sh = msm_shape(n, Curve::FrP::BITS, sizeof(Pt));
     if ((uint64_t)sh.nwin * n >= (1ull << 32)) return fail(c, B2S_ERR_INVALID_ARG, "msm: n * windows exceeds 2^32");
+    // batched-affine halving rounds (msm_affine.cuh); afterwards the points are already in bucket order.
+    // Rounds are worth it when buckets hold several points: R = ceil(log2(points per bucket)) rounds leave <= 2 points
+    // per average bucket for the XYZZ kernel; heavy buckets (skewed scalars) shrink by 2^R as well.
+    uint32_t ba_auto = 0;
+    {
+        const uint64_t per_bucket = ((uint64_t)sh.nwin * n) / sh.G;
+        while ((1ull << ba_auto) < per_bucket) ba_auto++;
+        if ((uint64_t)sh.nwin * n < (1ull << 16)) ba_auto = 0;            // tiny problems: launch overhead only
+    }
+    uint32_t ba_rounds = env_u32("B2S_MSM_AFFINE_ROUNDS", ba_auto);
+    // scratch of the rounds: two output buffers, the prefix products and the lane totals (bounded by the first round)
+    {
+        const uint64_t t0 = std::min<uint64_t>((uint64_t)sh.nwin * n, ((uint64_t)sh.nwin * n + sh.G) / 2 + 1);
+        const uint64_t need = t0 * (sizeof(Affine<F>) * 3 / 2 + sizeof(F)) + t0 / 4;
+        size_t free_b = 0, total_b = 0;
+        cudaMemGetInfo(&free_b, &total_b);
+        uint64_t pool_held = 0;
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, c->device) == cudaSuccess) {
+            uint64_t reserved = 0, used = 0;
+            cudaMemPoolGetAttribute(pool, cudaMemPoolAttrReservedMemCurrent, &reserved);
+            cudaMemPoolGetAttribute(pool, cudaMemPoolAttrUsedMemCurrent, &used);
+            pool_held = reserved > used ? reserved - used : 0;
+        }
+        if (ba_rounds && need + ((uint64_t)2 << 30) > (uint64_t)free_b + pool_held && !getenv("B2S_MSM_AFFINE_ROUNDS")) ba_rounds = 0;
+    }
+    if (ba_rounds && !getenv("B2S_MSM_L")) {
+        // what the XYZZ kernel sees after the rounds is 2^-R of the input: cut its tasks accordingly, otherwise the heavy
+        // buckets of skewed scalars (a few thousand tasks of ~1000 points) leave most of the machine idle
+        uint64_t t_after = (uint64_t)sh.nwin * n;
+        for (uint32_t r = 0; r < ba_rounds; r++) t_after = std::min<uint64_t>(t_after, (t_after + sh.G) / 2 + 1);
+        sh.L = (uint32_t)std::max<uint64_t>(16, t_after >> 18);
+        sh.max_tasks = t_after / sh.L + sh.G + 1;
+    }
     const Fr* scalars = reinterpret_cast<const Fr*>(scalars_dev);
     const Affine<F>* bases = reinterpret_cast<const Affine<F>*>(bases_dev);
 
@@ -477,32 +513,6 @@ static int32_t msm_run_t(Ctx* c, const void* bases_dev, const void* scalars_dev,
     B2S_LAUNCH(c, msm_scan_apply_kernel, ntiles, SCAN_THREADS, 0, counts, no_perm, sh, tiles.as<Scan3>(), offsets, task_off, heavy);
     B2S_LAUNCH(c, msm_scatter_kernel<Fr>, cdiv(n, 256), 256, 0, scalars, n, mont, sh, offsets, cursor, sorted.as<uint32_t>());
     constexpr bool is_g1 = sizeof(F) == sizeof(typename Curve::Fq);
-    // batched-affine halving rounds (msm_affine.cuh); afterwards the points are already in bucket order.
-    // Rounds are worth it when buckets hold several points: R = ceil(log2(points per bucket)) rounds leave <= 2 points
-    // per average bucket for the XYZZ kernel; heavy buckets (skewed scalars) shrink by 2^R as well.
-    uint32_t ba_auto = 0;
-    {
-        const uint64_t per_bucket = ((uint64_t)sh.nwin * n) / sh.G;
-        while ((1ull << ba_auto) < per_bucket) ba_auto++;
-        if ((uint64_t)sh.nwin * n < (1ull << 16)) ba_auto = 0;            // tiny problems: launch overhead only
-    }
-    uint32_t ba_rounds = env_u32("B2S_MSM_AFFINE_ROUNDS", ba_auto);
-    // scratch of the rounds: two output buffers, the prefix products and the lane totals (bounded by the first round)
-    {
-        const uint64_t t0 = ((uint64_t)sh.nwin * n + sh.G) / 2 + 1;
-        const uint64_t need = t0 * (sizeof(Affine<F>) * 3 / 2 + sizeof(F)) + t0 / 4;
-        size_t free_b = 0, total_b = 0;
-        cudaMemGetInfo(&free_b, &total_b);
-        uint64_t pool_held = 0;
-        cudaMemPool_t pool;
-        if (cudaDeviceGetDefaultMemPool(&pool, c->device) == cudaSuccess) {
-            uint64_t reserved = 0, used = 0;
-            cudaMemPoolGetAttribute(pool, cudaMemPoolAttrReservedMemCurrent, &reserved);
-            cudaMemPoolGetAttribute(pool, cudaMemPoolAttrUsedMemCurrent, &used);
-            pool_held = reserved > used ? reserved - used : 0;
-        }
-        if (ba_rounds && need + ((uint64_t)2 << 30) > (uint64_t)free_b + pool_held && !getenv("B2S_MSM_AFFINE_ROUNDS")) ba_rounds = 0;
-    }
     const void* acc_bases = bases;
     const uint32_t* acc_sorted = sorted.as<uint32_t>();
     const uint32_t* acc_offsets = offsets;
@@ -512,7 +522,9 @@ static int32_t msm_run_t(Ctx* c, const void* bases_dev, const void* scalars_dev,
         uint32_t* cnt[2] = {counts, ba_ints.as<uint32_t>()};
         uint32_t* off[2] = {offsets, ba_ints.as<uint32_t>() + sh.G};
         uint64_t t_in = (uint64_t)sh.nwin * n;
-        const uint64_t out_bound0 = (t_in + sh.G) / 2 + 1;
+        // outputs of a round: every bucket keeps ceil(count / 2) points -- at most (t_in + G) / 2 and never more than t_in
+        auto round_bound = [&](uint64_t tin) { return std::min<uint64_t>(tin, (tin + sh.G) / 2 + 1); };
+        const uint64_t out_bound0 = round_bound(t_in);
         const uint64_t words_bound0 = out_bound0 / 32 + 2;
         const uint64_t tot_bound = (words_bound0 / BA_KMIN + 2) * 32;
         const uint32_t rank_tiles0 = cdiv(words_bound0, BA_SCAN_TILE);
@@ -523,15 +535,18 @@ static int32_t msm_run_t(Ctx* c, const void* bases_dev, const void* scalars_dev,
         uint32_t* rtiles = wrank + words_bound0;
         B2S_TRY(ba_prefix.alloc(c, out_bound0 * sizeof(F)));
         B2S_TRY(ba_tot.alloc(c, 2 * tot_bound * sizeof(F)));
-        const uint32_t target_units = 4u * 12u * (uint32_t)c->sm_count;
+        const uint32_t target_units = 4u * 16u * (uint32_t)c->sm_count;   // ~4 units per resident warp, handed out dynamically
+        DevBuf ba_ctr;
+        B2S_TRY(ba_ctr.alloc(c, (size_t)2 * ba_rounds * sizeof(uint32_t)));
+        B2S_CUDA(c, cudaMemsetAsync(ba_ctr.p, 0, (size_t)2 * ba_rounds * sizeof(uint32_t), c->stream));
         // the two ping-pong output buffers, sized for the rounds that use them (even rounds write [1], odd rounds [0])
         B2S_TRY(ba_out[1].alloc(c, out_bound0 * sizeof(Affine<F>)));
-        if (ba_rounds > 1) B2S_TRY(ba_out[0].alloc(c, ((out_bound0 + sh.G) / 2 + 1) * sizeof(Affine<F>)));
+        if (ba_rounds > 1) B2S_TRY(ba_out[0].alloc(c, round_bound(out_bound0) * sizeof(Affine<F>)));
         int cur = 0;
         const void* prev = nullptr;
         for (uint32_t r = 0; r < ba_rounds; r++) {
             const int nxt = cur ^ 1;
-            const uint64_t out_bound = (t_in + sh.G) / 2 + 1;
+            const uint64_t out_bound = round_bound(t_in);
             const uint32_t n_words = (uint32_t)(out_bound / 32 + 2);
             const uint32_t rank_tiles = cdiv(n_words, BA_SCAN_TILE);
             B2S_LAUNCH(c, msm_ba_halve_kernel, cdiv(sh.G, 256), 256, 0, cnt[cur], sh.G, cnt[nxt]);
@@ -548,6 +563,7 @@ static int32_t msm_run_t(Ctx* c, const void* bases_dev, const void* scalars_dev,
             ra.bases = bases; ra.sorted = sorted.as<uint32_t>(); ra.prev = prev;
             ra.bitmap = bitmap; ra.wrank = wrank; ra.t_out = off[nxt] + sh.G;
             ra.target_units = target_units;
+            ra.unit_ctr = ba_ctr.as<uint32_t>() + 2 * r;
             ra.prefix = ba_prefix.p; ra.tot = ba_tot.p; ra.inv_scratch = ba_tot.as<F>() + tot_bound; ra.out = ba_out[nxt].p;
             if (is_g1) B2S_TRY(msm_ba_round_g1(c, ra));
             else B2S_TRY(msm_ba_round_g2(c, ra));

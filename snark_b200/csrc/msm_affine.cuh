@@ -37,7 +37,10 @@ enum : uint32_t { BA_F_VALID = 1u, BA_F_SINGLE = 2u };
 
 static constexpr uint32_t BA_KMIN = 16, BA_KMAX = 256;   // rows per unit (chosen on the device from the round's size)
 static constexpr uint32_t BA_K2 = 32;                     // lane totals per Fermat inversion
-static constexpr uint32_t BA_P1_STAGES = 4, BA_P2_STAGES = 2;
+#ifndef B2S_BA_P1_STAGES
+#define B2S_BA_P1_STAGES 3
+#endif
+static constexpr uint32_t BA_P1_STAGES = B2S_BA_P1_STAGES, BA_P2_STAGES = 2;
 
 __host__ __device__ constexpr uint32_t ba_slot_bytes(uint32_t n) { return ((((n + 15u) / 16u) | 1u)) * 16u; }
 
@@ -45,9 +48,12 @@ template <class F>
 struct BaGeom {
     static constexpr uint32_t FE = sizeof(F), PT = sizeof(Affine<F>);
     static constexpr uint32_t P1_META = 2 * FE, P1_SLOT = ba_slot_bytes(2 * FE + 16);
-    static constexpr uint32_t P2_PRE = 2 * PT, P2_META = 2 * PT + FE, P2_SLOT = ba_slot_bytes(2 * PT + FE + 16);
+    // pass 2 stages the two points only; the prefix product travels through registers (one row ahead) so that the slot
+    // ring of 16 warps fits an SM: occupancy is what hides the dependent-issue latency of the carry chains (ncu: `wait`)
+    static constexpr uint32_t P2_META = 2 * PT, P2_SLOT = ba_slot_bytes(2 * PT + 16);
     // threads per CTA: the G2 slots are twice as big, so half the threads keep three CTAs per SM
     static constexpr uint32_t THREADS = sizeof(F) > 64 ? 64 : 128;
+    static constexpr uint32_t P2_MIN_CTAS = 4;      // register cap of pass 2: 65536 / (THREADS * 4) = 128 (G1) / 256 (G2)
     static constexpr uint32_t P1_SMEM = THREADS * BA_P1_STAGES * P1_SLOT, P2_SMEM = THREADS * BA_P2_STAGES * P2_SLOT;
 };
 
@@ -117,6 +123,13 @@ __device__ __forceinline__ F ba_denominator(uint32_t kind, const Affine<F>& p1, 
     return F::one();
 }
 
+// units are handed out dynamically (one atomic per unit): warps that draw shorter rows or faster memory simply take more
+__device__ __forceinline__ uint32_t ba_next_unit(uint32_t* ctr, uint32_t lane) {
+    uint32_t u = 0;
+    if (lane == 0) u = atomicAdd(ctr, 1u);
+    return __shfl_sync(0xffffffffu, u, 0);
+}
+
 // descriptor of (row q, this lane): where its inputs are
 struct BaDesc { uint32_t in0, flags; };
 __device__ __forceinline__ BaDesc ba_desc(uint32_t word, uint32_t wr, uint32_t q, uint32_t lane, uint32_t t_out) {
@@ -155,7 +168,7 @@ template <class F, bool FIRST>
 __global__ void __launch_bounds__(BaGeom<F>::THREADS)
 msm_ba_p1_kernel(const Affine<F>* __restrict__ bases, const uint32_t* __restrict__ sorted, const Affine<F>* __restrict__ prev,
                  const uint32_t* __restrict__ bitmap, const uint32_t* __restrict__ wrank, const uint32_t* __restrict__ t_out_p,
-                 uint32_t target_units, F* __restrict__ prefix, F* __restrict__ tot) {
+                 uint32_t target_units, uint32_t* __restrict__ unit_ctr, F* __restrict__ prefix, F* __restrict__ tot) {
     using Gm = BaGeom<F>;
     constexpr uint32_t S = BA_P1_STAGES, FE = Gm::FE;
     extern __shared__ uint4 ba_smem[];
@@ -165,8 +178,7 @@ msm_ba_p1_kernel(const Affine<F>* __restrict__ bases, const uint32_t* __restrict
     const uint32_t n_rows = (t_out + 31u) >> 5;
     const uint32_t K = ba_rows_per_unit(n_rows, target_units);
     const uint32_t n_units = (n_rows + K - 1) / K;
-    const uint32_t warps_total = gridDim.x * (blockDim.x >> 5);
-    for (uint32_t u = blockIdx.x * (blockDim.x >> 5) + warp; u < n_units; u += warps_total) {
+    for (uint32_t u = ba_next_unit(unit_ctr, lane); u < n_units; u = ba_next_unit(unit_ctr, lane)) {
         const uint32_t q0 = u * K, nr = min(K, n_rows - q0);
         F prod = F::one();
         uint32_t a_word = 0, a_wr = 0;                 // stage A -> B
@@ -263,10 +275,11 @@ msm_ba_inv_kernel(F* __restrict__ tot, const uint32_t* __restrict__ t_out_p, uin
 // ---- pass 2 -------------------------------------------------------------------------------------------
 // Same pipeline as pass 1, rows in descending order (the running inverse walks the chain backwards).
 template <class F, bool FIRST>
-__global__ void __launch_bounds__(BaGeom<F>::THREADS)
+__global__ void __launch_bounds__(BaGeom<F>::THREADS, BaGeom<F>::P2_MIN_CTAS)
 msm_ba_p2_kernel(const Affine<F>* __restrict__ bases, const uint32_t* __restrict__ sorted, const Affine<F>* __restrict__ prev,
                  const uint32_t* __restrict__ bitmap, const uint32_t* __restrict__ wrank, const uint32_t* __restrict__ t_out_p,
-                 uint32_t target_units, const F* __restrict__ prefix, const F* __restrict__ tot_inv, Affine<F>* __restrict__ out) {
+                 uint32_t target_units, uint32_t* __restrict__ unit_ctr, const F* __restrict__ prefix, const F* __restrict__ tot_inv,
+                 Affine<F>* __restrict__ out) {
     using Gm = BaGeom<F>;
     constexpr uint32_t S = BA_P2_STAGES, FE = Gm::FE, PT = Gm::PT;
     extern __shared__ uint4 ba_smem[];
@@ -276,12 +289,16 @@ msm_ba_p2_kernel(const Affine<F>* __restrict__ bases, const uint32_t* __restrict
     const uint32_t n_rows = (t_out + 31u) >> 5;
     const uint32_t K = ba_rows_per_unit(n_rows, target_units);
     const uint32_t n_units = (n_rows + K - 1) / K;
-    const uint32_t warps_total = gridDim.x * (blockDim.x >> 5);
-    for (uint32_t u = blockIdx.x * (blockDim.x >> 5) + warp; u < n_units; u += warps_total) {
+    for (uint32_t u = ba_next_unit(unit_ctr, lane); u < n_units; u = ba_next_unit(unit_ctr, lane)) {
         const uint32_t q0 = u * K, nr = min(K, n_rows - q0);
         F inv = ld_struct(tot_inv + (size_t)u * 32u + lane);
         uint32_t a_word = 0, a_wr = 0, b_e1 = 0, b_e2 = 0;
         BaDesc b_d{0, 0};
+        F pre_next = F::one();    // prefix product of the row consumed next (fetched while the current row computes)
+        {
+            const uint32_t o0 = (q0 + nr - 1) * 32u + lane;
+            if (o0 < t_out) pre_next = ld_struct(prefix + o0);
+        }
         // step index i counts rows from the last one down: row q = q0 + nr - 1 - i
         for (int32_t t = -2; t < (int32_t)(nr + S); t++) {
             if (t >= (int32_t)S) {
@@ -289,6 +306,12 @@ msm_ba_p2_kernel(const Affine<F>* __restrict__ bases, const uint32_t* __restrict
                 const uint32_t i = (uint32_t)t - S;
                 const uint32_t slot = smem0 + (i % S) * 32u * Gm::P2_SLOT;
                 const uint4 meta = lds16(slot + Gm::P2_META);   // neg1, neg2, in0, flags
+                const F pre_cur = pre_next;
+                // the next row's prefix: requested now, used one row of arithmetic later
+                if (i + 1 < nr) {
+                    const uint32_t on = (q0 + nr - 2 - i) * 32u + lane;
+                    if (on < t_out) pre_next = ld_struct(prefix + on);
+                }
                 if (meta.w & BA_F_VALID) {
                     const bool single = (meta.w & BA_F_SINGLE) != 0;
                     const uint32_t o = (q0 + nr - 1 - i) * 32u + lane;
@@ -302,7 +325,7 @@ msm_ba_p2_kernel(const Affine<F>* __restrict__ bases, const uint32_t* __restrict
                     }
                     const uint32_t kind = ba_classify(p1, p2, single);
                     const F d = ba_denominator(kind, p1, p2);
-                    const F dinv = inv * lds_struct<F>(slot + Gm::P2_PRE);
+                    const F dinv = inv * pre_cur;
                     inv = inv * d;
                     Affine<F> res;
                     if (kind == BA_ADD || kind == BA_DBL) {
@@ -322,14 +345,12 @@ msm_ba_p2_kernel(const Affine<F>* __restrict__ bases, const uint32_t* __restrict
             if (t >= 0 && (uint32_t)t < nr) {
                 const uint32_t slot = smem0 + ((uint32_t)t % S) * 32u * Gm::P2_SLOT;
                 if (b_d.flags & BA_F_VALID) {
-                    const uint32_t o = (q0 + nr - 1 - (uint32_t)t) * 32u + lane;
                     const Affine<F>* a1 = FIRST ? bases + (b_e1 & 0x7fffffffu) : prev + b_d.in0;
                     cp_async_bytes<PT>(slot, a1);
                     if (!(b_d.flags & BA_F_SINGLE)) {
                         const Affine<F>* a2 = FIRST ? bases + (b_e2 & 0x7fffffffu) : prev + b_d.in0 + 1;
                         cp_async_bytes<PT>(slot + PT, a2);
                     }
-                    cp_async_bytes<FE>(slot + Gm::P2_PRE, prefix + o);
                 }
                 sts16(slot + Gm::P2_META, make_uint4(b_e1 >> 31, b_e2 >> 31, b_d.in0, b_d.flags));
             }
@@ -447,6 +468,7 @@ struct BaRoundArgs {
     const uint32_t* wrank;
     const uint32_t* t_out;        // device: number of outputs of this round
     uint32_t target_units;
+    uint32_t* unit_ctr;           // two zeroed counters (pass 1, pass 2)
     void* prefix;                 // F[t_out bound]
     void* tot;                    // F[lane totals bound]
     void* inv_scratch;            // F[lane totals bound]
@@ -462,27 +484,26 @@ static int32_t msm_ba_round_launch(Ctx* c, const char* l1, const char* li, const
     const Affine<F>* prev = reinterpret_cast<const Affine<F>*>(a.prev);
     F* prefix = reinterpret_cast<F*>(a.prefix);
     F* tot = reinterpret_cast<F*>(a.tot);
-    // persistent grids: as many CTAs as fit (shared-memory bound), units are handed out round-robin
-    const unsigned ctas1 = (unsigned)c->sm_count * max(1u, (220u * 1024u) / (Gm::P1_SMEM + 1024u));
-    const unsigned ctas2 = (unsigned)c->sm_count * max(1u, (220u * 1024u) / (Gm::P2_SMEM + 1024u));
+    // persistent grids: four CTAs per SM for both passes (16 warps; pass 2 is register- and shared-memory-bound there)
+    const unsigned ctas = 4u * (unsigned)c->sm_count;
     if (a.first) {
-        B2S_CUDA(c, cudaFuncSetAttribute(msm_ba_p1_kernel<F, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Gm::P1_SMEM));
-        B2S_CUDA(c, cudaFuncSetAttribute(msm_ba_p2_kernel<F, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Gm::P2_SMEM));
-        B2S_LAUNCH_N(c, l1, (msm_ba_p1_kernel<F, true>), ctas1, Gm::THREADS, Gm::P1_SMEM, bases, a.sorted, prev, a.bitmap, a.wrank, a.t_out,
-                     a.target_units, prefix, tot);
+        B2S_SMEM_ATTR(c, (msm_ba_p1_kernel<F, true>), Gm::P1_SMEM);
+        B2S_SMEM_ATTR(c, (msm_ba_p2_kernel<F, true>), Gm::P2_SMEM);
+        B2S_LAUNCH_N(c, l1, (msm_ba_p1_kernel<F, true>), ctas, Gm::THREADS, Gm::P1_SMEM, bases, a.sorted, prev, a.bitmap, a.wrank, a.t_out,
+                     a.target_units, a.unit_ctr, prefix, tot);
     } else {
-        B2S_CUDA(c, cudaFuncSetAttribute(msm_ba_p1_kernel<F, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Gm::P1_SMEM));
-        B2S_CUDA(c, cudaFuncSetAttribute(msm_ba_p2_kernel<F, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Gm::P2_SMEM));
-        B2S_LAUNCH_N(c, l1, (msm_ba_p1_kernel<F, false>), ctas1, Gm::THREADS, Gm::P1_SMEM, bases, a.sorted, prev, a.bitmap, a.wrank, a.t_out,
-                     a.target_units, prefix, tot);
+        B2S_SMEM_ATTR(c, (msm_ba_p1_kernel<F, false>), Gm::P1_SMEM);
+        B2S_SMEM_ATTR(c, (msm_ba_p2_kernel<F, false>), Gm::P2_SMEM);
+        B2S_LAUNCH_N(c, l1, (msm_ba_p1_kernel<F, false>), ctas, Gm::THREADS, Gm::P1_SMEM, bases, a.sorted, prev, a.bitmap, a.wrank, a.t_out,
+                     a.target_units, a.unit_ctr, prefix, tot);
     }
     B2S_LAUNCH_N(c, li, msm_ba_inv_kernel<F>, 4 * c->sm_count, 128, 0, tot, a.t_out, a.target_units, reinterpret_cast<F*>(a.inv_scratch));
     if (a.first)
-        B2S_LAUNCH_N(c, l2, (msm_ba_p2_kernel<F, true>), ctas2, Gm::THREADS, Gm::P2_SMEM, bases, a.sorted, prev, a.bitmap, a.wrank, a.t_out,
-                     a.target_units, (const F*)prefix, (const F*)tot, reinterpret_cast<Affine<F>*>(a.out));
+        B2S_LAUNCH_N(c, l2, (msm_ba_p2_kernel<F, true>), ctas, Gm::THREADS, Gm::P2_SMEM, bases, a.sorted, prev, a.bitmap, a.wrank, a.t_out,
+                     a.target_units, a.unit_ctr + 1, (const F*)prefix, (const F*)tot, reinterpret_cast<Affine<F>*>(a.out));
     else
-        B2S_LAUNCH_N(c, l2, (msm_ba_p2_kernel<F, false>), ctas2, Gm::THREADS, Gm::P2_SMEM, bases, a.sorted, prev, a.bitmap, a.wrank, a.t_out,
-                     a.target_units, (const F*)prefix, (const F*)tot, reinterpret_cast<Affine<F>*>(a.out));
+        B2S_LAUNCH_N(c, l2, (msm_ba_p2_kernel<F, false>), ctas, Gm::THREADS, Gm::P2_SMEM, bases, a.sorted, prev, a.bitmap, a.wrank, a.t_out,
+                     a.target_units, a.unit_ctr + 1, (const F*)prefix, (const F*)tot, reinterpret_cast<Affine<F>*>(a.out));
     return B2S_OK;
 }
 

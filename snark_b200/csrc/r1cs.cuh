@@ -39,10 +39,18 @@ int32_t pk_upload(Ctx* c, const b2s_pk_desc* d, int32_t mem, b2s_pk** out);
 int32_t groth16_setup(Ctx* c, const b2s_r1cs* m, const void* trapdoor_host, b2s_pk** out_pk, void* o_alpha_g1, void* o_beta_g2,
                       void* o_gamma_g2, void* o_delta_g2, void* o_gamma_abc);
 int32_t pk_query_download(Ctx* c, const b2s_pk* pk, int which, void* out_host, uint64_t cap_bytes);
-// z either as two host pieces (z_dev == nullptr) or as one device array
+// Where the h-query MSM of a shard takes its scalars from: the default computes the whole h on this GPU (replicated
+// witness_map); the multi-GPU group computes it distributed and hands back this rank's coefficient slab (group.cu).
+struct HSource {
+    // z_dev: the full assignment on the device.  On return *h_for_shard points at the scalars matching pk->h_query
+    // (pk->h_len elements starting at coefficient pk->h_off); the memory stays valid until the HSource is destroyed.
+    virtual int32_t get(Ctx* c, const b2s_pk* pk, const b2s_r1cs* m, const void* z_dev, const void** h_for_shard) = 0;
+    virtual ~HSource() = default;
+};
+// z either as two host pieces (z_dev == nullptr) or as one device array; hs == nullptr: replicated witness_map
 int32_t groth16_shard(Ctx* c, const b2s_pk* pk, const b2s_r1cs* m, const void* z_inst_host, const void* z_wit_host,
                       const void* z_dev, const void* r_host, const void* s_host, void* g1_partials_dev /*4 xyzz*/,
-                      void* g2_partial_dev /*1 xyzz*/);
+                      void* g2_partial_dev /*1 xyzz*/, HSource* hs = nullptr);
 int32_t groth16_finish(Ctx* c, const b2s_pk* pk, const void* g1_partials_dev, const void* g2_partials_dev, uint32_t n_shards,
                        const void* r_host, const void* s_host, void* out_a, void* out_b, void* out_c);
 }  // namespace b2s

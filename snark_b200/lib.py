@@ -60,6 +60,7 @@ SIGNATURES = {
     "b2s_spmv": (c_int32, [c_void_p, c_void_p, c_void_p, c_int32, c_void_p, c_void_p, c_void_p]),
     "b2s_witness_map": (c_int32, [c_void_p, c_void_p, c_void_p, c_int32, c_void_p]),
     "b2s_r1cs_domain_size": (c_uint64, [c_void_p]),
+    "b2s_witness_map_sim": (c_int32, [c_void_p, c_void_p, c_void_p, c_int32, c_uint32, c_void_p]),
     "b2s_pk_upload": (c_int32, [c_void_p, POINTER(PkDesc), c_int32, POINTER(c_void_p)]),
     "b2s_pk_free": (None, [c_void_p, c_void_p]),
     "b2s_groth16_setup": (c_int32, [c_void_p, c_void_p, c_void_p, POINTER(c_void_p)] + [c_void_p] * 5),
@@ -77,6 +78,11 @@ SIGNATURES = {
     "b2s_proof_serialize_compressed": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_uint64]),
     "b2s_fixed_base_g1": (c_int32, [c_void_p, c_void_p, c_uint64, c_int32, c_int32, c_void_p]),
     "b2s_fixed_base_g2": (c_int32, [c_void_p, c_void_p, c_uint64, c_int32, c_int32, c_void_p]),
+    "b2s_group_unique_id": (c_int32, [c_void_p]),
+    "b2s_group_create": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, POINTER(c_void_p)]),
+    "b2s_group_destroy": (None, [c_void_p]),
+    "b2s_groth16_prove_group": (c_int32, [c_void_p] * 10),
+    "b2s_groth16_prove_group_resident": (c_int32, [c_void_p] * 9),
     "b2s_field_op": (c_int32, [c_void_p, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_uint64]),
     "b2s_group_op": (c_int32, [c_void_p, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_uint64]),
 }
@@ -265,6 +271,14 @@ class Backend:
         self._ck(self.lib.b2s_witness_map(self.h, m, pz, mem, h.ctypes.data))
         return h
 
+    def witness_map_sim(self, m, z, log_ranks):
+        """witness_map by the distributed schedule with 2^log_ranks virtual ranks on this GPU (test entry)."""
+        pz, mem = _ptr(z)
+        assert mem == MEM_HOST
+        h = np.zeros(self.domain_size(m) * 8, dtype=np.uint32)
+        self._ck(self.lib.b2s_witness_map_sim(self.h, m, pz, mem, log_ranks, h.ctypes.data))
+        return h
+
     # ---- Groth16 ------------------------------------------------------------------------------
     def pk_upload(self, desc: PkDesc, mem=MEM_HOST):
         h = c_void_p()
@@ -345,6 +359,40 @@ class Backend:
         self._ck(self.lib.b2s_groth16_prove_shard(self.h, pk, m, _ptr(z_inst)[0], _ptr(z_wit)[0], r.ctypes.data, s.ctypes.data,
                                                   g1.ctypes.data, g2.ctypes.data))
         return g1, g2
+
+    # ---- multi-GPU group (NCCL inside the library) ----------------------------------------------
+    @staticmethod
+    def group_unique_id():
+        """128-byte NCCL id (rank 0 draws it; the host program distributes it)."""
+        buf = np.zeros(128, dtype=np.uint8)
+        st = load_library().b2s_group_unique_id(buf.ctypes.data)
+        if st != 0:
+            raise B2SError(st, "b2s_group_unique_id failed (NCCL not loadable?)")
+        return buf
+
+    def group_create(self, uid, rank, world):
+        g = c_void_p()
+        uid = np.ascontiguousarray(uid, dtype=np.uint8) if uid is not None else None
+        self._ck(self.lib.b2s_group_create(self.h, uid.ctypes.data if uid is not None else None, rank, world, ctypes.byref(g)))
+        return g
+
+    def group_destroy(self, g):
+        self.lib.b2s_group_destroy(g)
+
+    def groth16_prove_group(self, g, pk, m, z_inst, z_wit, r, s):
+        """Collective over the group; the proof (a, b, c) is meaningful on rank 0."""
+        a, b, c = self._proof_bufs()
+        st = self.lib.b2s_groth16_prove_group(g, pk, m, _ptr(z_inst)[0], _ptr(z_wit)[0], r.ctypes.data, s.ctypes.data, a.ctypes.data,
+                                              b.ctypes.data, c.ctypes.data)
+        self._ck(st)
+        return a, b, c
+
+    def groth16_prove_group_resident(self, g, pk, m, z_dev, r, s):
+        a, b, c = self._proof_bufs()
+        st = self.lib.b2s_groth16_prove_group_resident(g, pk, m, _ptr(z_dev)[0], r.ctypes.data, s.ctypes.data, a.ctypes.data,
+                                                       b.ctypes.data, c.ctypes.data)
+        self._ck(st)
+        return a, b, c
 
     def groth16_finish(self, pk, g1_partials, g2_partials, n_shards, r, s):
         a, b, c = self._proof_bufs()

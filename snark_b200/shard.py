@@ -12,6 +12,14 @@ def shard_range(total, rank, world):
     return total * rank // world, total * (rank + 1) // world
 
 
+def slab_range(domain_size, rank, world):
+    """h-query shard = the coefficient slab [rank N/G, (rank+1) N/G) of h (clipped to the N - 1 query points): the layout
+    the distributed witness map (csrc/dntt.cu) delivers, so no redistribution of h is needed before its MSM."""
+    per = domain_size // world
+    lo = per * rank
+    return lo, min(lo + per, domain_size - 1)
+
+
 QUERIES = (  # (descriptor field, offset field, length field, group, which length)
     ("a_query", "a_off", "a_len", 1, "n_vars"),
     ("b_g1_query", "b1_off", "b1_len", 1, "n_vars"),
@@ -30,7 +38,7 @@ def shard_plan(n_instance, n_witness, domain_size, rank, world):
     tot = query_totals(n_instance, n_witness, domain_size)
     plan = {}
     for name, _, _, _, which in QUERIES:
-        lo, hi = shard_range(tot[which], rank, world)
+        lo, hi = slab_range(domain_size, rank, world) if which == "h" else shard_range(tot[which], rank, world)
         plan[name] = (lo, hi - lo)
     return plan
 

@@ -28,7 +28,7 @@ def test_roofline_from_report():
     assert abs(roof["frac"] - d["roofline"]["frac"]) < 1e-4 and 0.85 < roof["alu"]["frac"] < 1.0
     # with the batched-affine rounds the three round launches and the XYZZ pass count as one unit per MSM
     rep2 = dict(rep)
-    rep2["msm_ba_round_g1"] = (12 * d["steps"], 249.6 * d["steps"])
+    rep2["msm_ba_p2_g1"] = (12 * d["steps"], 249.6 * d["steps"])
     rep2["msm_accumulate_g1"] = (4 * d["steps"], 48.3 * d["steps"])
     roof2 = bench.roofline_from_report(rep2, 1 << 24, 1, 24, 6569.6, "measured")
     assert roof2["traffic"] is None and roof2["launch_unit"].startswith("one MSM")
@@ -67,6 +67,13 @@ def test_reference_arm_prints_one_contract_line():
     assert d["e2e"] == {"value": d["value"], "unit": "proofs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["value"] == d["value"] and d["cpu_baseline"]["cores"] >= 1
     assert "workload" in d["config"] and abs(d["ms_per_step"] - 1e3 / d["value"]) < 1e-6 * d["ms_per_step"]
+    # a sample smaller than the stated configuration: the line carries the step time AS RUN and says it is extrapolated
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--log-n", "12", "--ref-log-n", "10",
+                          "--steps", "1", "--warmup", "0"], capture_output=True, text=True, timeout=600, cwd=root)
+    d = json.loads([l for l in out.stdout.splitlines() if l.strip()][0])
+    assert d["extrapolated"] is True and 0 < d["sample_fraction_of_config"] < 1
+    assert abs(d["ms_per_step"] * d["value"] / 1e3 - d["sample_fraction_of_config"]) < 1e-9
+    assert abs(d["ms_per_step_extrapolated_to_config"] - 1e3 / d["value"]) < 1e-6 * d["ms_per_step_extrapolated_to_config"]
     # a non-zero rank of a torchrun launch prints nothing
     quiet = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--log-n", "10", "--ref-log-n", "10",
                             "--steps", "1", "--warmup", "0"], capture_output=True, text=True, timeout=600, cwd=root,

@@ -153,3 +153,87 @@ def test_groth16_shards_join(be):
     for h in handles:
         be.pk_free(h)
     be.r1cs_free(m)
+
+
+def _shard_desc(be, full, idx, nshards):
+    from snark_b200.lib import PkDesc
+
+    g1b, g2b = be.g1_bytes, be.g2_bytes
+    d = PkDesc()
+    for f in ("n_instance", "n_witness", "domain_size", "alpha_g1", "beta_g1", "delta_g1", "beta_g2", "delta_g2"):
+        setattr(d, f, getattr(full, f))
+    for q, off, ln, sz in (("a_query", "a_off", "a_len", g1b), ("b_g1_query", "b1_off", "b1_len", g1b), ("b_g2_query", "b2_off", "b2_len", g2b),
+                           ("h_query", "h_off", "h_len", g1b), ("l_query", "l_off", "l_len", g1b)):
+        total = getattr(full, ln)
+        lo, hi = total * idx // nshards, total * (idx + 1) // nshards
+        setattr(d, q, getattr(full, q) + lo * sz)
+        setattr(d, off, lo)
+        setattr(d, ln, hi - lo)
+    return d
+
+
+def test_group_of_one_equals_single_prove(be):
+    """b2s_groth16_prove_group with world = 1 (no NCCL involved): the packed all-gather layout and the strided join give
+    the single-GPU proof."""
+    curve = CURVES[be.curve]
+    rng = random.Random(15)
+    mats, inst, wit = orc.dummy_circuit_direct(curve, rng.randrange(curve.r), rng.randrange(curve.r), 24, 24)
+    td = og.Trapdoor(*[rng.randrange(1, curve.r) for _ in range(5)])
+    pk = og.setup(curve, mats, len(inst), len(wit), td)
+    rr, ss = rng.randrange(curve.r), rng.randrange(curve.r)
+    A, B, C, _ = og.prove(pk, mats, inst, wit, rr, ss)
+    m, _keep = upload(be, curve, mats, len(inst), len(wit))
+    keep = []
+    pkh = be.pk_upload(make_pk_desc(curve, pk, keep))
+    grp = be.group_create(None, 0, 1)
+    a, b, c = be.groth16_prove_group(grp, pkh, m, pack_fr(curve, inst), pack_fr(curve, wit), pack_fr(curve, [rr]), pack_fr(curve, [ss]))
+    assert (unpack_points(curve, 1, a)[0], unpack_points(curve, 2, b)[0], unpack_points(curve, 1, c)[0]) == (A, B, C)
+    be.group_destroy(grp)
+    be.pk_free(pkh)
+    be.r1cs_free(m)
+
+
+def test_group_of_two_devices_one_process():
+    """Two ctxs on two GPUs of one process (one host thread each), joined by the library's own NCCL communicator: the
+    proof equals the oracle's.  Also covers a second ctx on another device needing the > 48 KiB shared-memory attributes
+    of the NTT / MSM kernels (they are per device).  Skipped on a one-GPU box."""
+    import threading
+
+    import torch
+
+    from snark_b200 import Backend
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    curve = CURVES[0]
+    rng = random.Random(25)
+    mats, inst, wit = orc.dummy_circuit_direct(curve, rng.randrange(curve.r), rng.randrange(curve.r), 40, 40)
+    td = og.Trapdoor(*[rng.randrange(1, curve.r) for _ in range(5)])
+    pk = og.setup(curve, mats, len(inst), len(wit), td)
+    rr, ss = rng.randrange(curve.r), rng.randrange(curve.r)
+    A, B, C, _ = og.prove(pk, mats, inst, wit, rr, ss)
+    uid = Backend.group_unique_id()
+    out, errs = {}, []
+
+    def rank_main(rk):
+        try:
+            b = Backend(curve=0, device=rk)
+            m, _k = upload(b, curve, mats, len(inst), len(wit))
+            keep = []
+            pkh = b.pk_upload(_shard_desc(b, make_pk_desc(curve, pk, keep), rk, 2))
+            grp = b.group_create(uid, rk, 2)
+            res = b.groth16_prove_group(grp, pkh, m, pack_fr(curve, inst), pack_fr(curve, wit), pack_fr(curve, [rr]), pack_fr(curve, [ss]))
+            if rk == 0:
+                out["proof"] = res
+            b.group_destroy(grp); b.pk_free(pkh); b.r1cs_free(m); b.close()
+        except Exception as e:   # noqa: BLE001 -- reported by the main thread
+            errs.append((rk, repr(e)))
+
+    ts = [threading.Thread(target=rank_main, args=(rk,)) for rk in range(2)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join(timeout=300)
+    assert not errs, errs
+    a, b_, c = out["proof"]
+    assert (unpack_points(curve, 1, a)[0], unpack_points(curve, 2, b_)[0], unpack_points(curve, 1, c)[0]) == (A, B, C)

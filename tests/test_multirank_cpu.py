@@ -21,7 +21,12 @@ def test_shard_ranges_partition():
             assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
             assert max(hi - lo for lo, hi in spans) - min(hi - lo for lo, hi in spans) <= 1
     plan = shard.shard_plan(2, 13, 16, 1, 2)
-    assert plan == {"a_query": (7, 8), "b_g1_query": (7, 8), "b_g2_query": (7, 8), "h_query": (7, 8), "l_query": (6, 7)}
+    # h is cut by coefficient slab [r N/G, (r+1) N/G) (clipped to the N - 1 query points), the others by base range
+    assert plan == {"a_query": (7, 8), "b_g1_query": (7, 8), "b_g2_query": (7, 8), "h_query": (8, 7), "l_query": (6, 7)}
+    for world in (1, 2, 4, 8):
+        spans = [shard.slab_range(1 << 10, r, world) for r in range(world)]
+        assert spans[0][0] == 0 and spans[-1][1] == (1 << 10) - 1 and all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+        assert all(lo == r * (1 << 10) // world for r, (lo, _) in enumerate(spans))
 
 
 def _worker(rank, world, port, q):
