@@ -446,9 +446,12 @@ def run_b200(args):
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    dev_ms, wall_ms, launches, rep, proof_a = timed(True, args.steps, args.warmup, profile=True)
+    dev_ms, wall_ms, launches, _, proof_a = timed(True, args.steps, args.warmup)
     clocks = sampler.stop() if rank == 0 else None
     e2e_ms, e2e_wall, _, _, proof_b = timed(False, args.steps, 1)
+    # per-kernel breakdown from a separate profiled pass (an event pair around each of the ~1000 launches of a proof costs
+    # tens of milliseconds per step, so it stays out of the two timed regions above)
+    _, _, _, rep, _ = timed(True, 1, 0, profile=True)
 
     if rank != 0:
         if world > 1:
@@ -489,7 +492,7 @@ def run_b200(args):
         "e2e": {"value": e2e_value, "unit": "proofs/s", "h2d_bytes_per_step": int(n_vars * 32 + 64), "d2h_bytes_per_step": int(2 * g1w + g2w),
                 "ms_per_step": e2e_ms / args.steps},
         "gpu_launches": launches, "clocks": clocks, "roofline": roof,
-        "kernel_ms_per_step": {k: round(v[1] / args.steps, 4) for k, v in sorted(rep.items(), key=lambda kv: -kv[1][1])},
+        "kernel_ms_per_step": {k: round(v[1], 4) for k, v in sorted(rep.items(), key=lambda kv: -kv[1][1])},
         "msm_g1_adds_per_sec_in_prove": msm_adds, "wall_ms_per_step": wall_ms / args.steps,
         "verified": verified,
     }

@@ -228,6 +228,26 @@ int32_t b2s_serialize_g2_compressed(b2s_ctx* ctx, const void* affine, uint32_t c
 int32_t b2s_proof_serialize_compressed(b2s_ctx* ctx, const void* a_g1, const void* b_g2, const void* c_g1, uint8_t* out,
                                        uint64_t cap);
 
+/* serialize_uncompressed of the same types: x || y in the curve's byte / component order (96 / 192 B on BLS12-381 with only
+ * the infinity bit in byte 0; 64 / 128 B on BN254 with both SWFlags in the last byte). */
+int32_t b2s_serialize_g1_uncompressed(b2s_ctx* ctx, const void* affine, uint32_t count, uint8_t* out, uint64_t cap);
+int32_t b2s_serialize_g2_uncompressed(b2s_ctx* ctx, const void* affine, uint32_t count, uint8_t* out, uint64_t cap);
+int32_t b2s_proof_serialize_uncompressed(b2s_ctx* ctx, const void* a_g1, const void* b_g2, const void* c_g1, uint8_t* out,
+                                         uint64_t cap);
+/* ark-groth16 key framing (snark/src/lib.rs:25-36: ProvingKey / VerifyingKey are CanonicalSerialize):
+ *   VerifyingKey = alpha_g1 || beta_g2 || gamma_g2 || delta_g2 || Vec(gamma_abc_g1)       (Vec = u64 LE length + elements)
+ *   ProvingKey   = VerifyingKey || beta_g1 || delta_g1 || Vec(a_query) || Vec(b_g1_query) || Vec(b_g2_query) ||
+ *                  Vec(h_query) || Vec(l_query)
+ * The vk elements are HOST affine points (what b2s_groth16_setup wrote); the proving key is the device-resident FULL key,
+ * streamed through the GPU in chunks (canonical form and sign bits on the device, byte order on the host).
+ * compressed = 1 / 0 selects serialize_compressed / serialize_uncompressed.  The *_size functions give the exact length. */
+uint64_t b2s_vk_serialized_size(const b2s_ctx* ctx, uint64_t n_gamma_abc, int32_t compressed);
+int32_t b2s_vk_serialize(b2s_ctx* ctx, const void* alpha_g1, const void* beta_g2, const void* gamma_g2, const void* delta_g2,
+                         const void* gamma_abc_g1, uint64_t n_gamma_abc, int32_t compressed, uint8_t* out, uint64_t cap);
+uint64_t b2s_pk_serialized_size(const b2s_ctx* ctx, const b2s_pk* pk, uint64_t vk_len, int32_t compressed);
+int32_t b2s_pk_serialize(b2s_ctx* ctx, const b2s_pk* pk, const uint8_t* vk_bytes, uint64_t vk_len, int32_t compressed,
+                         uint8_t* out, uint64_t cap);
+
 /* ---- setup helper: fixed-base batch multiplication -------------------------
  * out[i] = scalars[i] * G (the curve's standard generator), affine, i < n.  Used to build proving keys
  * (a_query[j] = A_j(tau) G1, ...) and synthetic bases on the GPU.  scalars: Fr; all buffers share `mem`. */

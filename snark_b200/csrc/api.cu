@@ -18,6 +18,12 @@ int32_t group_op_run(Ctx* c, int group, int op, const void* a, const void* b, co
 int32_t fixed_base_run(Ctx* c, int group, const void* scalars_dev, uint64_t n, bool mont, void* out_dev);
 void fixed_base_free(Ctx* c);
 int32_t serialize_points(Ctx* c, int group, const void* affine_host, uint32_t count, uint8_t* out, uint64_t cap);
+int32_t serialize_points_ex(Ctx* c, int group, const void* affine, int32_t mem, uint64_t count, bool compressed, uint8_t* out, uint64_t cap);
+uint64_t vk_serialized_size(Ctx* c, uint64_t n_gamma_abc, bool compressed);
+int32_t vk_serialize(Ctx* c, const void* alpha_g1, const void* beta_g2, const void* gamma_g2, const void* delta_g2, const void* gamma_abc,
+                     uint64_t n_gamma_abc, bool compressed, uint8_t* out, uint64_t cap);
+uint64_t pk_serialized_size(Ctx* c, const b2s_pk* pk, uint64_t vk_len, bool compressed);
+int32_t pk_serialize(Ctx* c, const b2s_pk* pk, const uint8_t* vk_bytes, uint64_t vk_len, bool compressed, uint8_t* out, uint64_t cap);
 }  // namespace b2s
 
 #define LOCK(ctx)                                      \
@@ -490,6 +496,45 @@ int32_t b2s_serialize_g2_compressed(b2s_ctx* ctx, const void* affine, uint32_t c
     if ((!affine || !out) && count) return fail(ctx, B2S_ERR_INVALID_ARG, "serialize: null buffer");
     return serialize_points(ctx, 2, affine, count, out, cap);
 }
+int32_t b2s_serialize_g1_uncompressed(b2s_ctx* ctx, const void* affine, uint32_t count, uint8_t* out, uint64_t cap) {
+    LOCK(ctx);
+    if ((!affine || !out) && count) return fail(ctx, B2S_ERR_INVALID_ARG, "serialize: null buffer");
+    return serialize_points_ex(ctx, 1, affine, B2S_MEM_HOST, count, false, out, cap);
+}
+int32_t b2s_serialize_g2_uncompressed(b2s_ctx* ctx, const void* affine, uint32_t count, uint8_t* out, uint64_t cap) {
+    LOCK(ctx);
+    if ((!affine || !out) && count) return fail(ctx, B2S_ERR_INVALID_ARG, "serialize: null buffer");
+    return serialize_points_ex(ctx, 2, affine, B2S_MEM_HOST, count, false, out, cap);
+}
+int32_t b2s_proof_serialize_uncompressed(b2s_ctx* ctx, const void* a_g1, const void* b_g2, const void* c_g1, uint8_t* out, uint64_t cap) {
+    LOCK(ctx);
+    if (!a_g1 || !b_g2 || !c_g1 || !out) return fail(ctx, B2S_ERR_INVALID_ARG, "proof_serialize: null buffer");
+    const uint64_t fq = ctx->curve == B2S_CURVE_BLS12_381 ? 48 : 32;
+    if (cap < 8 * fq) return fail(ctx, B2S_ERR_INVALID_ARG, "proof_serialize: output buffer too small");
+    B2S_TRY(serialize_points_ex(ctx, 1, a_g1, B2S_MEM_HOST, 1, false, out, 2 * fq));
+    B2S_TRY(serialize_points_ex(ctx, 2, b_g2, B2S_MEM_HOST, 1, false, out + 2 * fq, 4 * fq));
+    return serialize_points_ex(ctx, 1, c_g1, B2S_MEM_HOST, 1, false, out + 6 * fq, 2 * fq);
+}
+uint64_t b2s_vk_serialized_size(const b2s_ctx* ctx, uint64_t n_gamma_abc, int32_t compressed) {
+    return ctx ? vk_serialized_size(const_cast<b2s_ctx*>(ctx), n_gamma_abc, compressed != 0) : 0;
+}
+int32_t b2s_vk_serialize(b2s_ctx* ctx, const void* alpha_g1, const void* beta_g2, const void* gamma_g2, const void* delta_g2,
+                         const void* gamma_abc_g1, uint64_t n_gamma_abc, int32_t compressed, uint8_t* out, uint64_t cap) {
+    LOCK(ctx);
+    if (!alpha_g1 || !beta_g2 || !gamma_g2 || !delta_g2 || (!gamma_abc_g1 && n_gamma_abc) || !out)
+        return fail(ctx, B2S_ERR_INVALID_ARG, "vk_serialize: null buffer");
+    return vk_serialize(ctx, alpha_g1, beta_g2, gamma_g2, delta_g2, gamma_abc_g1, n_gamma_abc, compressed != 0, out, cap);
+}
+uint64_t b2s_pk_serialized_size(const b2s_ctx* ctx, const b2s_pk* pk, uint64_t vk_len, int32_t compressed) {
+    return (ctx && pk) ? pk_serialized_size(const_cast<b2s_ctx*>(ctx), pk, vk_len, compressed != 0) : 0;
+}
+int32_t b2s_pk_serialize(b2s_ctx* ctx, const b2s_pk* pk, const uint8_t* vk_bytes, uint64_t vk_len, int32_t compressed, uint8_t* out,
+                         uint64_t cap) {
+    LOCK(ctx);
+    if (!pk || (!vk_bytes && vk_len) || !out) return fail(ctx, B2S_ERR_INVALID_ARG, "pk_serialize: null argument");
+    return pk_serialize(ctx, pk, vk_bytes, vk_len, compressed != 0, out, cap);
+}
+
 int32_t b2s_proof_serialize_compressed(b2s_ctx* ctx, const void* a_g1, const void* b_g2, const void* c_g1, uint8_t* out,
                                        uint64_t cap) {
     LOCK(ctx);

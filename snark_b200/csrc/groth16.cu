@@ -20,46 +20,53 @@
 // partial sums; the rank that owns the END of a query range also owns its two extra pairs.  The join adds
 // the partials (EC addition is not an NCCL reduction, so the exchange is an all-gather of 5 small points)
 // and applies the epilogue.
+#include "ec_team.cuh"
 #include "r1cs.cuh"
 
 namespace b2s {
 
-// Warps 0, 1, 2 run the three remaining scalar multiplications side by side.
+// Warps 0, 1, 2 run the three remaining scalar multiplications side by side (4-bit windows, four-lane teams of
+// ec_team.cuh: a doubling costs 3 multiplication latencies instead of 9); warp 3 normalises A meanwhile.
 template <class Curve>
-__global__ void groth16_epilogue_g1_kernel(const Affine<typename Curve::Fq>* consts /*alpha,beta,delta*/,
-                                           const XYZZ<typename Curve::Fq>* sums /*h,l,a,b1*/, const typename Curve::Fr* rs,
-                                           Affine<typename Curve::Fq>* out_a, Affine<typename Curve::Fq>* out_c) {
+__global__ void __launch_bounds__(128)
+groth16_epilogue_g1_kernel(const Affine<typename Curve::Fq>* consts /*alpha,beta,delta*/, const XYZZ<typename Curve::Fq>* sums /*h,l,a,b1*/,
+                           const typename Curve::Fr* rs, Affine<typename Curve::Fq>* out_a, Affine<typename Curve::Fq>* out_c) {
     using Fq = typename Curve::Fq;
     using Fr = typename Curve::Fr;
     using P = XYZZ<Fq>;
     __shared__ P sh[3];
+    __shared__ P table[3][16];
     const int role = threadIdx.x >> 5;
     const bool lead = (threadIdx.x & 31) == 0;
-    if (lead && role == 0) {   // s * A,  A = alpha + a_acc
+    if (role == 0) {   // s * A,  A = alpha + a_acc
         P a = sums[2];
         a.add_affine(consts[0]);
-        *out_a = a.to_affine();
         Fr s = rs[1].from_mont();
-        sh[0] = scalar_mul_words(a, s.v, Fr::N);
-    }
-    if (lead && role == 1) {   // r * B1,  B1 = beta + b1_acc
+        P v = team_scalar_mul(a, s.v, Fr::N, table[0]);
+        if (lead) sh[0] = v;
+    } else if (role == 1) {   // r * B1,  B1 = beta + b1_acc
         P b = sums[3];
         b.add_affine(consts[1]);
         Fr r = rs[0].from_mont();
-        sh[1] = scalar_mul_words(b, r.v, Fr::N);
-    }
-    if (lead && role == 2) {   // (r s) * delta
+        P v = team_scalar_mul(b, r.v, Fr::N, table[1]);
+        if (lead) sh[1] = v;
+    } else if (role == 2) {   // (r s) * delta
         Fr rsp = (rs[0] * rs[1]).from_mont();
-        sh[2] = scalar_mul_words(P::from_affine(consts[2]), rsp.v, Fr::N);
+        P v = team_scalar_mul(P::from_affine(consts[2]), rsp.v, Fr::N, table[2]);
+        if (lead) sh[2] = v;
+    } else {   // A itself, normalised (one inversion) while the others multiply
+        P a = sums[2];
+        a.add_affine(consts[0]);
+        if (lead) *out_a = a.to_affine();
     }
     __syncthreads();
-    if (threadIdx.x == 0) {
+    if (role == 0) {
         P c = sh[0];
-        c.add(sh[1]);
-        c.add(sh[2].neg());
-        c.add(sums[1]);
-        c.add(sums[0]);
-        *out_c = c.to_affine();
+        team_add(c, sh[1]);
+        team_add(c, sh[2].neg());
+        team_add(c, sums[1]);
+        team_add(c, sums[0]);
+        if (lead) *out_c = c.to_affine();
     }
 }
 
@@ -229,7 +236,7 @@ static int32_t finish_t(Ctx* c, const b2s_pk* pk, const void* g1_partials, uint3
     const size_t g1 = sizeof(Affine<Fq>), g2 = sizeof(Affine<Fq2>);
     B2S_TRY(outs.alloc(c, 2 * g1 + g2));
     char* o = outs.as<char>();
-    B2S_LAUNCH(c, groth16_epilogue_g1_kernel<Curve>, 1, 96, 0, pk->consts_g1.as<Affine<Fq>>(), sums1.as<XYZZ<Fq>>(), rs.as<Fr>(),
+    B2S_LAUNCH(c, groth16_epilogue_g1_kernel<Curve>, 1, 128, 0, pk->consts_g1.as<Affine<Fq>>(), sums1.as<XYZZ<Fq>>(), rs.as<Fr>(),
                reinterpret_cast<Affine<Fq>*>(o), reinterpret_cast<Affine<Fq>*>(o + g1));
     B2S_LAUNCH(c, groth16_epilogue_g2_kernel<Curve>, 1, 32, 0, pk->consts_g2.as<Affine<Fq2>>(), sums2.as<XYZZ<Fq2>>(),
                reinterpret_cast<Affine<Fq2>*>(o + 2 * g1));

@@ -268,27 +268,6 @@ __global__ void msm_scatter_kernel(const Fr* __restrict__ scalars, uint64_t n, b
     }
 }
 
-// Sum `count` XYZZ points with one CTA; result in out[0] (also used by the join of shard partials).
-template <class F>
-__device__ __forceinline__ XYZZ<F> cta_sum(const XYZZ<F>* __restrict__ pts, uint32_t count, XYZZ<F>* smem) {
-    XYZZ<F> acc = XYZZ<F>::identity();
-    for (uint32_t i = threadIdx.x; i < count; i += blockDim.x) {
-        XYZZ<F> v = ld_struct(pts + i);
-        acc.add(v);
-    }
-    smem[threadIdx.x] = acc;
-    __syncthreads();
-    for (uint32_t d = blockDim.x >> 1; d > 0; d >>= 1) {
-        if (threadIdx.x < d) {
-            XYZZ<F> a = smem[threadIdx.x];
-            a.add(smem[threadIdx.x + d]);
-            smem[threadIdx.x] = a;
-        }
-        __syncthreads();
-    }
-    return smem[0];
-}
-
 // Buckets that were split into tasks: sum their task partials.  Big ones (>= HEAVY_BIG partials, e.g. the
 // one-bucket-per-window case of an all-equal witness) first get HEAVY_SPLIT CTAs each, which leave their
 // slice sums in tmp[t0 / HEAVY_SPLIT + j] (t0 = first task of the bucket; slots of different big buckets
@@ -331,52 +310,6 @@ msm_reduce_heavy_kernel(const uint32_t* __restrict__ heavy, const uint32_t* __re
     }
 }
 
-// k * p for a small non-negative integer k (double-and-add, most significant bit first)
-template <class F>
-__device__ __forceinline__ XYZZ<F> mul_small(const XYZZ<F>& p, uint32_t k) {
-    XYZZ<F> acc = XYZZ<F>::identity();
-    if (k == 0 || p.is_identity()) return acc;
-    for (int b = 31 - __clz(k); b >= 0; b--) {
-        acc = acc.dbl();
-        if ((k >> b) & 1) acc.add(p);
-    }
-    return acc;
-}
-
-// Segment sums: thread handles buckets [s0, s0 + MSM_SEG) of one window (MSM_SEG chosen by the host) (bucket index b is 0-based,
-// weight b + 1):  sum (b+1) B_b = sum_{local} (j+1) B_{s0+j} + s0 * sum B_{s0+j}.
-template <class F>
-__global__ void __launch_bounds__(128)
-msm_bucket_segments_kernel(const XYZZ<F>* __restrict__ bucket_acc, MsmShape sh, uint32_t MSM_SEG, XYZZ<F>* __restrict__ seg_out) {
-    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-    const uint32_t segs_per_win = (sh.B + MSM_SEG - 1) / MSM_SEG;
-    if (t >= segs_per_win * sh.nwin) return;
-    const uint32_t w = t / segs_per_win, sg = t % segs_per_win;
-    const uint32_t s0 = sg * MSM_SEG, s1 = min(s0 + MSM_SEG, sh.B);
-    const XYZZ<F>* bk = bucket_acc + (size_t)w * sh.B;
-    XYZZ<F> run = XYZZ<F>::identity(), acc = XYZZ<F>::identity();
-    for (uint32_t j = s1; j-- > s0;) {
-        XYZZ<F> v = ld_struct(bk + j);
-        run.add(v);
-        acc.add(run);
-    }
-    if (s0 != 0) {
-        XYZZ<F> m = mul_small(run, s0);
-        acc.add(m);
-    }
-    st_struct(seg_out + t, acc);
-}
-
-// One CTA per window: S_w = sum of its segment results.
-template <class F>
-__global__ void __launch_bounds__(MSM_RED_THREADS)
-msm_window_sum_kernel(const XYZZ<F>* __restrict__ seg, uint32_t segs_per_win, XYZZ<F>* __restrict__ win_out) {
-    extern __shared__ uint4 smem_raw[];
-    XYZZ<F>* smem = reinterpret_cast<XYZZ<F>*>(smem_raw);
-    XYZZ<F> s = cta_sum(seg + (size_t)blockIdx.x * segs_per_win, segs_per_win, smem);
-    if (threadIdx.x == 0) st_struct(win_out + blockIdx.x, s);
-}
-
 // sum of `count` XYZZ points -> affine (join of multi-GPU shard partials; final normalisation)
 template <class F>
 __global__ void __launch_bounds__(MSM_RED_THREADS)
@@ -388,6 +321,15 @@ group_sum_affine_kernel(const XYZZ<F>* __restrict__ pts, uint32_t count, Affine<
         Affine<F> a = s.to_affine();
         st_struct(out, a);
     }
+}
+
+// G2 bucket reduction stays in this unit (out-of-line multiplication): inlining 42 base multiplications per general
+// addition into its kernels costs a quarter of an hour of ptxas for a ~5 % kernel
+int32_t msm_bucket_reduce_g2(Ctx* c, const void* bucket_acc, MsmShape sh, uint32_t seg, void* segs, uint32_t segs_per_win, void* wins) {
+    return dispatch_curve(c, [&](auto curve) {
+        using F = typename decltype(curve)::Fq2;
+        return msm_bucket_reduce_launch<F>(c, "msm_bucket_segments_g2", "msm_window_sum_g2", bucket_acc, sh, seg, segs, segs_per_win, wins);
+    });
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -442,6 +384,7 @@ static int32_t msm_run_t(Ctx* c, const void* bases_dev, const void* scalars_dev,
         B2S_CUDA(c, cudaMemsetAsync(out, 0, sizeof(Pt), c->stream));
         return B2S_OK;
     }
+    constexpr bool is_g1_t = sizeof(F) == sizeof(typename Curve::Fq);
     MsmShape sh = msm_shape(n, Curve::FrP::BITS, sizeof(Pt));
     if ((uint64_t)sh.nwin * n >= (1ull << 32)) return fail(c, B2S_ERR_INVALID_ARG, "msm: n * windows exceeds 2^32");
     // batched-affine halving rounds (msm_affine.cuh); afterwards the points are already in bucket order.
@@ -451,7 +394,12 @@ static int32_t msm_run_t(Ctx* c, const void* bases_dev, const void* scalars_dev,
     {
         const uint64_t per_bucket = ((uint64_t)sh.nwin * n) / sh.G;
         while ((1ull << ba_auto) < per_bucket) ba_auto++;
-        if ((uint64_t)sh.nwin * n < (1ull << 16)) ba_auto = 0;            // tiny problems: launch overhead only
+        // a round has a fixed price -- one latency-bound inversion level (~0.7 ms) plus a dozen small launches -- and
+        // saves 4 (G1) / 11 (G2) base multiplications on each of its T / 2^(r+1) additions: keep the rounds that pay
+        const double min_adds = is_g1_t ? 6.0e6 : 2.5e6;
+        uint32_t pays = 0;
+        while (pays < 16 && (double)((uint64_t)sh.nwin * n >> (pays + 1)) > min_adds) pays++;
+        ba_auto = std::min(ba_auto, pays);
     }
     uint32_t ba_rounds = env_u32("B2S_MSM_AFFINE_ROUNDS", ba_auto);
     // scratch of the rounds: two output buffers, the prefix products and the lane totals (bounded by the first round)
@@ -598,14 +546,13 @@ static int32_t msm_run_t(Ctx* c, const void* bases_dev, const void* scalars_dev,
     const size_t red_smem = (size_t)MSM_RED_THREADS * sizeof(Pt);
     B2S_SMEM_ATTR(c, msm_reduce_heavy_kernel<F>, red_smem);
     B2S_SMEM_ATTR(c, msm_reduce_heavy_stage1_kernel<F>, red_smem);
-    B2S_SMEM_ATTR(c, msm_window_sum_kernel<F>, red_smem);
     B2S_LAUNCH(c, msm_reduce_heavy_stage1_kernel<F>, 4 * c->sm_count, MSM_RED_THREADS, red_smem, heavy, task_off,
                partials.as<Pt>(), heavy_tmp.as<Pt>());
     B2S_LAUNCH(c, msm_reduce_heavy_kernel<F>, 2 * c->sm_count, MSM_RED_THREADS, red_smem, heavy, task_off, perm,
                partials.as<Pt>(), heavy_tmp.as<Pt>(), bucket_acc.as<Pt>());
-    B2S_LAUNCH(c, msm_bucket_segments_kernel<F>, cdiv((uint64_t)segs_per_win * sh.nwin, 128), 128, 0,
-               bucket_acc.as<Pt>(), sh, MSM_SEG, segs.as<Pt>());
-    B2S_LAUNCH(c, msm_window_sum_kernel<F>, sh.nwin, MSM_RED_THREADS, red_smem, segs.as<Pt>(), segs_per_win, wins_p);
+    // bucket reduction: compiled with the multiplication inlined (msm_acc_g1.cu / msm_acc_g2.cu), 2 general additions per bucket
+    if (is_g1) B2S_TRY(msm_bucket_reduce_g1(c, bucket_acc.p, sh, MSM_SEG, segs.p, segs_per_win, wins_p));
+    else B2S_TRY(msm_bucket_reduce_g2(c, bucket_acc.p, sh, MSM_SEG, segs.p, segs_per_win, wins_p));
     if (!wins_ext) {
         B2S_TRY(msm_horner(c, c->stream, is_g1 ? 1 : 2, wins_p, sh, out));
     } else {

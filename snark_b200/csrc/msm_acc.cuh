@@ -3,6 +3,7 @@
 // prover) and msm.cu (G2, out-of-line multiplication).
 #pragma once
 #include "common.cuh"
+#include "ec_team.cuh"
 
 #ifndef B2S_G2_MIN_BLOCKS
 #define B2S_G2_MIN_BLOCKS 1   // CTAs/SM the G2 accumulate kernel is compiled for (register cap = 65536 / (128 * this))
@@ -122,18 +123,99 @@ msm_accumulate_kernel(const Affine<F>* __restrict__ bases, const uint32_t* __res
 }
 
 
-// result = sum_w 2^(c w) S_w  (Horner from the top window).
+// result = sum_w 2^(c w) S_w  (Horner from the top window): ~250 dependent doublings, the longest serial chain of an MSM.
+// One warp; the four-lane teams of ec_team.cuh cut a doubling from 9 multiplication latencies to 3.
 template <class F>
-__global__ void msm_horner_kernel(const XYZZ<F>* __restrict__ win, MsmShape sh, XYZZ<F>* __restrict__ out) {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+__global__ void __launch_bounds__(32) msm_horner_kernel(const XYZZ<F>* __restrict__ win, MsmShape sh, XYZZ<F>* __restrict__ out) {
     XYZZ<F> acc = ld_struct(win + (sh.nwin - 1));
     for (uint32_t w = sh.nwin - 1; w-- > 0;) {
-        for (uint32_t i = 0; i < sh.c; i++) acc = acc.dbl();
+        for (uint32_t i = 0; i < sh.c; i++) team_dbl(acc);
         XYZZ<F> v = ld_struct(win + w);
+        team_add(acc, v);
+    }
+    if (threadIdx.x == 0) st_struct(out, acc);
+}
+
+// Sum `count` XYZZ points with one CTA; result in out[0] (also used by the join of shard partials).
+template <class F>
+__device__ __forceinline__ XYZZ<F> cta_sum(const XYZZ<F>* __restrict__ pts, uint32_t count, XYZZ<F>* smem) {
+    XYZZ<F> acc = XYZZ<F>::identity();
+    for (uint32_t i = threadIdx.x; i < count; i += blockDim.x) {
+        XYZZ<F> v = ld_struct(pts + i);
         acc.add(v);
     }
-    st_struct(out, acc);
+    smem[threadIdx.x] = acc;
+    __syncthreads();
+    for (uint32_t d = blockDim.x >> 1; d > 0; d >>= 1) {
+        if (threadIdx.x < d) {
+            XYZZ<F> a = smem[threadIdx.x];
+            a.add(smem[threadIdx.x + d]);
+            smem[threadIdx.x] = a;
+        }
+        __syncthreads();
+    }
+    return smem[0];
 }
+
+// k * p for a small non-negative integer k (double-and-add, most significant bit first)
+template <class F>
+__device__ __forceinline__ XYZZ<F> mul_small(const XYZZ<F>& p, uint32_t k) {
+    XYZZ<F> acc = XYZZ<F>::identity();
+    if (k == 0 || p.is_identity()) return acc;
+    for (int b = 31 - __clz(k); b >= 0; b--) {
+        acc = acc.dbl();
+        if ((k >> b) & 1) acc.add(p);
+    }
+    return acc;
+}
+
+// Segment sums: thread handles buckets [s0, s0 + MSM_SEG) of one window (MSM_SEG chosen by the host) (bucket index b is 0-based,
+// weight b + 1):  sum (b+1) B_b = sum_{local} (j+1) B_{s0+j} + s0 * sum B_{s0+j}.
+template <class F>
+__global__ void __launch_bounds__(128)
+msm_bucket_segments_kernel(const XYZZ<F>* __restrict__ bucket_acc, MsmShape sh, uint32_t MSM_SEG, XYZZ<F>* __restrict__ seg_out) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t segs_per_win = (sh.B + MSM_SEG - 1) / MSM_SEG;
+    if (t >= segs_per_win * sh.nwin) return;
+    const uint32_t w = t / segs_per_win, sg = t % segs_per_win;
+    const uint32_t s0 = sg * MSM_SEG, s1 = min(s0 + MSM_SEG, sh.B);
+    const XYZZ<F>* bk = bucket_acc + (size_t)w * sh.B;
+    XYZZ<F> run = XYZZ<F>::identity(), acc = XYZZ<F>::identity();
+    for (uint32_t j = s1; j-- > s0;) {
+        XYZZ<F> v = ld_struct(bk + j);
+        run.add(v);
+        acc.add(run);
+    }
+    if (s0 != 0) {
+        XYZZ<F> m = mul_small(run, s0);
+        acc.add(m);
+    }
+    st_struct(seg_out + t, acc);
+}
+
+// One CTA per window: S_w = sum of its segment results.
+template <class F>
+__global__ void __launch_bounds__(MSM_RED_THREADS)
+msm_window_sum_kernel(const XYZZ<F>* __restrict__ seg, uint32_t segs_per_win, XYZZ<F>* __restrict__ win_out) {
+    extern __shared__ uint4 smem_raw[];
+    XYZZ<F>* smem = reinterpret_cast<XYZZ<F>*>(smem_raw);
+    XYZZ<F> s = cta_sum(seg + (size_t)blockIdx.x * segs_per_win, segs_per_win, smem);
+    if (threadIdx.x == 0) st_struct(win_out + blockIdx.x, s);
+}
+
+template <class F>
+static int32_t msm_bucket_reduce_launch(Ctx* c, const char* l_seg, const char* l_win, const void* bucket_acc, MsmShape sh, uint32_t seg, void* segs,
+                                        uint32_t segs_per_win, void* wins) {
+    using Pt = XYZZ<F>;
+    const size_t red_smem = (size_t)MSM_RED_THREADS * sizeof(Pt);
+    B2S_SMEM_ATTR(c, msm_window_sum_kernel<F>, red_smem);
+    B2S_LAUNCH_N(c, l_seg, msm_bucket_segments_kernel<F>, cdiv((uint64_t)segs_per_win * sh.nwin, 128), 128, 0, reinterpret_cast<const Pt*>(bucket_acc), sh, seg,
+                 reinterpret_cast<Pt*>(segs));
+    B2S_LAUNCH_N(c, l_win, msm_window_sum_kernel<F>, sh.nwin, MSM_RED_THREADS, red_smem, reinterpret_cast<const Pt*>(segs), segs_per_win, reinterpret_cast<Pt*>(wins));
+    return B2S_OK;
+}
+int32_t msm_bucket_reduce_g1(Ctx* c, const void* bucket_acc, MsmShape sh, uint32_t seg, void* segs, uint32_t segs_per_win, void* wins);
+int32_t msm_bucket_reduce_g2(Ctx* c, const void* bucket_acc, MsmShape sh, uint32_t seg, void* segs, uint32_t segs_per_win, void* wins);
 
 // launches compiled with the multiplication inlined: msm_acc_g1.cu (G1) and msm_acc_g2.cu (G2)
 int32_t msm_accumulate_g2(Ctx* c, const void* bases, const uint32_t* sorted, const uint32_t* offsets,

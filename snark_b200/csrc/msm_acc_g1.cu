@@ -32,4 +32,11 @@ int32_t msm_ba_round_g1(Ctx* c, const BaRoundArgs& a) {
     });
 }
 
+int32_t msm_bucket_reduce_g1(Ctx* c, const void* bucket_acc, MsmShape sh, uint32_t seg, void* segs, uint32_t segs_per_win, void* wins) {
+    return dispatch_curve(c, [&](auto curve) {
+        using F = typename decltype(curve)::Fq;
+        return msm_bucket_reduce_launch<F>(c, "msm_bucket_segments_g1", "msm_window_sum_g1", bucket_acc, sh, seg, segs, segs_per_win, wins);
+    });
+}
+
 }  // namespace b2s

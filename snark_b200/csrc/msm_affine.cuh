@@ -28,6 +28,8 @@
 //     barrier is needed -- cp.async.wait_group orders a lane's copies before its reads.
 //     Slot stride = odd multiple of 16 B: conflict-free for the 16-byte shared-memory accesses used throughout.
 #pragma once
+#include <algorithm>
+
 #include "msm_acc.cuh"
 
 namespace b2s {
@@ -486,15 +488,16 @@ static int32_t msm_ba_round_launch(Ctx* c, const char* l1, const char* li, const
     F* tot = reinterpret_cast<F*>(a.tot);
     // persistent grids: four CTAs per SM for both passes (16 warps; pass 2 is register- and shared-memory-bound there)
     const unsigned ctas = 4u * (unsigned)c->sm_count;
+    const unsigned ctas1 = (unsigned)c->sm_count * std::max(1u, std::min(5u, (224u * 1024u) / (Gm::P1_SMEM + 1024u)));   // pass 1 is lighter
     if (a.first) {
         B2S_SMEM_ATTR(c, (msm_ba_p1_kernel<F, true>), Gm::P1_SMEM);
         B2S_SMEM_ATTR(c, (msm_ba_p2_kernel<F, true>), Gm::P2_SMEM);
-        B2S_LAUNCH_N(c, l1, (msm_ba_p1_kernel<F, true>), ctas, Gm::THREADS, Gm::P1_SMEM, bases, a.sorted, prev, a.bitmap, a.wrank, a.t_out,
+        B2S_LAUNCH_N(c, l1, (msm_ba_p1_kernel<F, true>), ctas1, Gm::THREADS, Gm::P1_SMEM, bases, a.sorted, prev, a.bitmap, a.wrank, a.t_out,
                      a.target_units, a.unit_ctr, prefix, tot);
     } else {
         B2S_SMEM_ATTR(c, (msm_ba_p1_kernel<F, false>), Gm::P1_SMEM);
         B2S_SMEM_ATTR(c, (msm_ba_p2_kernel<F, false>), Gm::P2_SMEM);
-        B2S_LAUNCH_N(c, l1, (msm_ba_p1_kernel<F, false>), ctas, Gm::THREADS, Gm::P1_SMEM, bases, a.sorted, prev, a.bitmap, a.wrank, a.t_out,
+        B2S_LAUNCH_N(c, l1, (msm_ba_p1_kernel<F, false>), ctas1, Gm::THREADS, Gm::P1_SMEM, bases, a.sorted, prev, a.bitmap, a.wrank, a.t_out,
                      a.target_units, a.unit_ctr, prefix, tot);
     }
     B2S_LAUNCH_N(c, li, msm_ba_inv_kernel<F>, 4 * c->sm_count, 128, 0, tot, a.t_out, a.target_units, reinterpret_cast<F*>(a.inv_scratch));

@@ -76,6 +76,13 @@ SIGNATURES = {
     "b2s_serialize_g1_compressed": (c_int32, [c_void_p, c_void_p, c_uint32, c_void_p, c_uint64]),
     "b2s_serialize_g2_compressed": (c_int32, [c_void_p, c_void_p, c_uint32, c_void_p, c_uint64]),
     "b2s_proof_serialize_compressed": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_uint64]),
+    "b2s_serialize_g1_uncompressed": (c_int32, [c_void_p, c_void_p, c_uint32, c_void_p, c_uint64]),
+    "b2s_serialize_g2_uncompressed": (c_int32, [c_void_p, c_void_p, c_uint32, c_void_p, c_uint64]),
+    "b2s_proof_serialize_uncompressed": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_uint64]),
+    "b2s_vk_serialized_size": (c_uint64, [c_void_p, c_uint64, c_int32]),
+    "b2s_vk_serialize": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_uint64, c_int32, c_void_p, c_uint64]),
+    "b2s_pk_serialized_size": (c_uint64, [c_void_p, c_void_p, c_uint64, c_int32]),
+    "b2s_pk_serialize": (c_int32, [c_void_p, c_void_p, c_void_p, c_uint64, c_int32, c_void_p, c_uint64]),
     "b2s_fixed_base_g1": (c_int32, [c_void_p, c_void_p, c_uint64, c_int32, c_int32, c_void_p]),
     "b2s_fixed_base_g2": (c_int32, [c_void_p, c_void_p, c_uint64, c_int32, c_int32, c_void_p]),
     "b2s_group_unique_id": (c_int32, [c_void_p]),
@@ -302,16 +309,31 @@ class Backend:
         self._ck(self.lib.b2s_pk_query(self.h, pk, which, out.ctypes.data, out.nbytes))
         return out
 
-    def serialize_points(self, group, affine, count):
-        per = (self.fq_bytes if group == 1 else 2 * self.fq_bytes)
+    def serialize_points(self, group, affine, count, compressed=True):
+        per = (self.fq_bytes if group == 1 else 2 * self.fq_bytes) * (1 if compressed else 2)
         out = np.zeros(count * per, dtype=np.uint8)
-        fn = self.lib.b2s_serialize_g1_compressed if group == 1 else self.lib.b2s_serialize_g2_compressed
-        self._ck(fn(self.h, affine.ctypes.data, count, out.ctypes.data, out.nbytes))
+        name = f"b2s_serialize_g{group}_{'compressed' if compressed else 'uncompressed'}"
+        self._ck(getattr(self.lib, name)(self.h, affine.ctypes.data, count, out.ctypes.data, out.nbytes))
         return out.tobytes()
 
-    def proof_bytes(self, a, b, c):
-        out = np.zeros(4 * self.fq_bytes, dtype=np.uint8)
-        self._ck(self.lib.b2s_proof_serialize_compressed(self.h, a.ctypes.data, b.ctypes.data, c.ctypes.data, out.ctypes.data, out.nbytes))
+    def proof_bytes(self, a, b, c, compressed=True):
+        out = np.zeros(4 * self.fq_bytes * (1 if compressed else 2), dtype=np.uint8)
+        fn = self.lib.b2s_proof_serialize_compressed if compressed else self.lib.b2s_proof_serialize_uncompressed
+        self._ck(fn(self.h, a.ctypes.data, b.ctypes.data, c.ctypes.data, out.ctypes.data, out.nbytes))
+        return out.tobytes()
+
+    def vk_bytes(self, alpha_g1, beta_g2, gamma_g2, delta_g2, gamma_abc_g1, n_gamma_abc, compressed=True):
+        """ark-groth16 VerifyingKey bytes from the HOST affine points b2s_groth16_setup returned."""
+        out = np.zeros(int(self.lib.b2s_vk_serialized_size(self.h, n_gamma_abc, int(compressed))), dtype=np.uint8)
+        self._ck(self.lib.b2s_vk_serialize(self.h, alpha_g1.ctypes.data, beta_g2.ctypes.data, gamma_g2.ctypes.data, delta_g2.ctypes.data,
+                                           gamma_abc_g1.ctypes.data, n_gamma_abc, int(compressed), out.ctypes.data, out.nbytes))
+        return out.tobytes()
+
+    def pk_bytes(self, pk, vk_bytes, compressed=True):
+        """ark-groth16 ProvingKey bytes of a device-resident full key (vk_bytes from vk_bytes())."""
+        vk = np.frombuffer(vk_bytes, dtype=np.uint8)
+        out = np.zeros(int(self.lib.b2s_pk_serialized_size(self.h, pk, len(vk), int(compressed))), dtype=np.uint8)
+        self._ck(self.lib.b2s_pk_serialize(self.h, pk, vk.ctypes.data, len(vk), int(compressed), out.ctypes.data, out.nbytes))
         return out.tobytes()
 
     def pk_free(self, pk):

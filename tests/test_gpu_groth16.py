@@ -166,6 +166,9 @@ def _shard_desc(be, full, idx, nshards):
                            ("h_query", "h_off", "h_len", g1b), ("l_query", "l_off", "l_len", g1b)):
         total = getattr(full, ln)
         lo, hi = total * idx // nshards, total * (idx + 1) // nshards
+        if q == "h_query":     # coefficient slabs: what the distributed witness map of the group hands each rank
+            per = full.domain_size // nshards
+            lo, hi = per * idx, min(per * (idx + 1), full.domain_size - 1)
         setattr(d, q, getattr(full, q) + lo * sz)
         setattr(d, off, lo)
         setattr(d, ln, hi - lo)

@@ -25,6 +25,15 @@ def be(request):
     b.close()
 
 
+@pytest.fixture(params=[None, 3], ids=["rounds_auto", "rounds_3"])
+def affine_rounds(request, monkeypatch):
+    """The batched-affine halving rounds (csrc/msm_affine.cuh) switch themselves on only where they pay (large MSMs);
+    `rounds_3` forces three rounds so that the small inputs and every edge case below run through them as well."""
+    if request.param is not None:
+        monkeypatch.setenv("B2S_MSM_AFFINE_ROUNDS", str(request.param))
+    return request.param
+
+
 def gpu_msm(be, curve, group, bases, scalars, mont=True):
     B = pack_points(curve, group, bases)
     S = pack_fr(curve, scalars, mont=mont)
@@ -33,7 +42,7 @@ def gpu_msm(be, curve, group, bases, scalars, mont=True):
 
 
 @pytest.mark.parametrize("group", [1, 2])
-def test_msm_small_vs_oracle(be, group):
+def test_msm_small_vs_oracle(be, group, affine_rounds):
     curve = CURVES[be.curve]
     G = groups(curve)[group - 1]
     rng = random.Random(11 * group)
@@ -48,7 +57,7 @@ def test_msm_small_vs_oracle(be, group):
 
 
 @pytest.mark.parametrize("group", [1, 2])
-def test_msm_edge_cases(be, group):
+def test_msm_edge_cases(be, group, affine_rounds):
     curve = CURVES[be.curve]
     G = groups(curve)[group - 1]
     rng = random.Random(3)
@@ -88,7 +97,7 @@ def test_msm_window_sizes(be, monkeypatch):
 
 
 @pytest.mark.parametrize("group,log_n", [(1, 14), (1, 18), (2, 14)])
-def test_msm_known_discrete_logs(be, group, log_n):
+def test_msm_known_discrete_logs(be, group, log_n, affine_rounds):
     """Random scalars; bases (i+1)*G built on the GPU by the fixed-base kernel."""
     import torch
 
