@@ -38,6 +38,25 @@ extern "C" {
     pub fn b2s_groth16_prove(ctx: *mut B2sCtx, pk: *const B2sPk, m: *const B2sR1cs, z_inst: *const c_void,
                              z_wit: *const c_void, r: *const c_void, s: *const c_void, out_a: *mut c_void,
                              out_b: *mut c_void, out_c: *mut c_void) -> i32;
+    // multi-GPU group (one rank per GPU, NCCL communicator inside the library)
+    pub fn b2s_group_unique_id(out: *mut u8) -> i32; // 128 bytes
+    pub fn b2s_group_create(ctx: *mut B2sCtx, id: *const u8, rank: i32, world: i32, out: *mut *mut B2sGroup) -> i32;
+    pub fn b2s_group_destroy(group: *mut B2sGroup);
+    pub fn b2s_groth16_prove_group(group: *mut B2sGroup, pk_shard: *const B2sPk, m: *const B2sR1cs, z_inst: *const c_void,
+                                   z_wit: *const c_void, r: *const c_void, s: *const c_void, out_a: *mut c_void,
+                                   out_b: *mut c_void, out_c: *mut c_void) -> i32;
+    // CanonicalSerialize of the key types (snark/src/lib.rs:25-31)
+    pub fn b2s_vk_serialized_size(ctx: *const B2sCtx, n_gamma_abc: u64, compressed: i32) -> u64;
+    pub fn b2s_vk_serialize(ctx: *mut B2sCtx, alpha_g1: *const c_void, beta_g2: *const c_void, gamma_g2: *const c_void,
+                            delta_g2: *const c_void, gamma_abc_g1: *const c_void, n_gamma_abc: u64, compressed: i32,
+                            out: *mut u8, cap: u64) -> i32;
+    pub fn b2s_pk_serialized_size(ctx: *const B2sCtx, pk: *const B2sPk, vk_len: u64, compressed: i32) -> u64;
+    pub fn b2s_pk_serialize(ctx: *mut B2sCtx, pk: *const B2sPk, vk_bytes: *const u8, vk_len: u64, compressed: i32,
+                            out: *mut u8, cap: u64) -> i32;
+}
+#[repr(C)]
+pub struct B2sGroup {
+    _p: [u8; 0],
 }
 
 #[derive(Debug)]

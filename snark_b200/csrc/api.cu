@@ -57,6 +57,9 @@ int32_t b2s_ctx_create(int32_t curve_id, int32_t device_ordinal, b2s_ctx** out) 
     c->sm_count = prop.multiProcessorCount;
     if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaStreamCreateWithFlags(&c->aux, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&c->side, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&c->ev_tail, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&c->ev_done, cudaEventDisableTiming) != cudaSuccess) {
         delete c;
@@ -87,6 +90,10 @@ void b2s_ctx_destroy(b2s_ctx* ctx) {
     fixed_base_free(ctx);
     cudaStreamSynchronize(ctx->stream);
     cudaStreamSynchronize(ctx->aux);
+    cudaStreamSynchronize(ctx->side);
+    cudaEventDestroy(ctx->ev_fork);
+    cudaEventDestroy(ctx->ev_join);
+    cudaStreamDestroy(ctx->side);
     cudaEventDestroy(ctx->ev_tail);
     cudaEventDestroy(ctx->ev_done);
     cudaStreamDestroy(ctx->aux);

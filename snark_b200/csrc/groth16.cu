@@ -198,14 +198,37 @@ static int32_t shard_t(Ctx* c, const b2s_pk* pk, const b2s_r1cs* m, const void* 
     P1* g1 = reinterpret_cast<P1*>(g1_out);
     P1* w1 = tails.as<P1>();
     void* w2 = w1 + 4 * 64;
-    // the MSMs that only need z go first (their Horner tails run on the aux stream under the following work);
-    // G2 first because its tail is the longest
+    // Fork: the witness map (SpMV, seven transforms, quotient -- or its distributed form) is enqueued on the side stream and
+    // runs side by side with the four MSMs that only need z; the h-query MSM joins them.  The ctx's launch stream is swapped
+    // for the duration of the enqueue (everything below the C ABI launches and allocates on c->stream).
+    const void* h_shard = nullptr;
+    const bool fork = !getenv("B2S_NO_SIDE_STREAM");
+    struct SideGuard {   // an error return must not leave work in flight on the side stream over buffers being released
+        Ctx* c; cudaStream_t main; bool active;
+        ~SideGuard() { if (active) { c->stream = main; cudaStreamSynchronize(c->side); } }
+    } side_guard{c, c->stream, false};
+    if (fork) {
+        B2S_CUDA(c, cudaEventRecord(c->ev_fork, c->stream));
+        B2S_CUDA(c, cudaStreamWaitEvent(c->side, c->ev_fork, 0));
+        side_guard.active = true;
+        c->stream = c->side;
+        const int32_t st = hs->get(c, pk, m, zd, &h_shard);
+        c->stream = side_guard.main;
+        if (st != B2S_OK) return st;
+        B2S_CUDA(c, cudaEventRecord(c->ev_join, c->side));
+    }
+    // the MSMs that only need z (their Horner tails run on the aux stream under the following work); G2 first because its
+    // tail is the longest
     B2S_TRY(msm_run(c, 2, pk->b_g2_query.p, zd + pk->b2_off, pk->b2_len + pk->b2_ext, true, g2_out, w2));
     B2S_TRY(msm_run(c, 1, pk->a_query.p, zd + pk->a_off, pk->a_len + pk->a_ext, true, g1 + 2, w1 + 2 * 64));
     B2S_TRY(msm_run(c, 1, pk->b_g1_query.p, zd + pk->b1_off, pk->b1_len + pk->b1_ext, true, g1 + 3, w1 + 3 * 64));
     B2S_TRY(msm_run(c, 1, pk->l_query.p, zd + m->n_instance + pk->l_off, pk->l_len, true, g1 + 1, w1 + 1 * 64));
-    const void* h_shard = nullptr;
-    B2S_TRY(hs->get(c, pk, m, zd, &h_shard));
+    if (fork) {
+        B2S_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_join, 0));
+        side_guard.active = false;
+    } else {
+        B2S_TRY(hs->get(c, pk, m, zd, &h_shard));
+    }
     B2S_TRY(msm_run(c, 1, pk->h_query.p, h_shard, pk->h_len, true, g1 + 0, w1 + 0 * 64));
     B2S_TRY(msm_join_tails(c));
     return B2S_OK;

@@ -29,6 +29,8 @@
 // costs ceil(255/c) mixed additions of ~10 Fq multiplications = ~3000 wide IMADs; the kernel is
 // bound by the fma pipe by two orders of magnitude over HBM (DESIGN.md has the numbers).
 #include <algorithm>
+#include <array>
+#include <cstring>
 
 #include "msm_affine.cuh"
 
@@ -244,7 +246,7 @@ msm_scan_apply_kernel(const uint32_t* __restrict__ counts, const uint32_t* __res
 }
 
 template <class Fr>
-__global__ void msm_scatter_kernel(const Fr* __restrict__ scalars, uint64_t n, bool mont, MsmShape sh,
+__global__ void msm_scatter_kernel(const Fr* __restrict__ scalars, const uint32_t* __restrict__ index_map, uint64_t n, bool mont, MsmShape sh,
                                    const uint32_t* __restrict__ offsets, uint32_t* __restrict__ cursor,
                                    uint32_t* __restrict__ sorted) {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -253,6 +255,7 @@ __global__ void msm_scatter_kernel(const Fr* __restrict__ scalars, uint64_t n, b
     const unsigned lane = threadIdx.x & 31;
     DigitIter it;
     load_scalar(it, scalars, i, mont);
+    const uint32_t base_idx = index_map ? index_map[i] : (uint32_t)i;
     for (uint32_t w = 0; w < sh.nwin; w++) {
         const int32_t d = it.next(w, sh.c, sh.nwin);
         const uint32_t key = d != 0 ? w * sh.B + (uint32_t)(d < 0 ? -d : d) - 1 : 0xffffffffu;
@@ -263,39 +266,46 @@ __global__ void msm_scatter_kernel(const Fr* __restrict__ scalars, uint64_t n, b
         base = __shfl_sync(peers, base, leader);
         if (key != 0xffffffffu) {
             const uint32_t rank = __popc(peers & ((1u << lane) - 1u));
-            sorted[offsets[key] + base + rank] = (uint32_t)i | (d < 0 ? 0x80000000u : 0u);
+            sorted[offsets[key] + base + rank] = base_idx | (d < 0 ? 0x80000000u : 0u);
         }
     }
 }
 
-// Buckets that were split into tasks: sum their task partials.  Big ones (>= HEAVY_BIG partials, e.g. the
-// one-bucket-per-window case of an all-equal witness) first get HEAVY_SPLIT CTAs each, which leave their
-// slice sums in tmp[t0 / HEAVY_SPLIT + j] (t0 = first task of the bucket; slots of different big buckets
-// cannot overlap because each owns >= HEAVY_BIG consecutive tasks); then one CTA per bucket finishes.
-static constexpr uint32_t HEAVY_SPLIT = 16;
-static constexpr uint32_t HEAVY_BIG = 16 * HEAVY_SPLIT;
+// Buckets that were split into tasks: sum their task partials.  Big ones (>= `big` partials, e.g. the
+// one-bucket-per-window case of an all-equal witness) first get `split` CTAs each, which leave their slice sums in tmp;
+// then one CTA per bucket finishes.  Slot of (heavy bucket h, slice j):
+//   many buckets (the Pippenger bucket array): tmp[t0 / split + j], t0 = first task of the bucket; slots of different big
+//     buckets cannot overlap because each owns >= big = split^2 consecutive tasks (split = 16);
+//   few buckets (the <= 8 heavy lists of the multiplicity-aware front end): tmp[h * split + j] with split = 256, so that one
+//     list's hundreds of thousands of partials are summed by 256 CTAs instead of 16.
+struct HeavyPlan { uint32_t split, big, by_ordinal; };
+static HeavyPlan heavy_plan(uint32_t G) { return G <= 64 ? HeavyPlan{256u, 512u, 1u} : HeavyPlan{16u, 256u, 0u}; }
+static size_t heavy_tmp_slots(const HeavyPlan& hp, uint32_t G, uint64_t max_tasks) {
+    return hp.by_ordinal ? (size_t)G * hp.split + 1 : (size_t)(max_tasks / hp.split) + hp.split + 1;
+}
 
 template <class F>
 __global__ void __launch_bounds__(MSM_RED_THREADS)
-msm_reduce_heavy_stage1_kernel(const uint32_t* __restrict__ heavy, const uint32_t* __restrict__ task_off,
+msm_reduce_heavy_stage1_kernel(const uint32_t* __restrict__ heavy, const uint32_t* __restrict__ task_off, HeavyPlan hp,
                                const XYZZ<F>* __restrict__ partials, XYZZ<F>* __restrict__ tmp) {   // heavy[] holds ranks
     extern __shared__ uint4 smem_raw[];
     XYZZ<F>* smem = reinterpret_cast<XYZZ<F>*>(smem_raw);
-    const uint32_t nitems = heavy[0] * HEAVY_SPLIT;
+    const uint32_t nitems = heavy[0] * hp.split;
     for (uint32_t it = blockIdx.x; it < nitems; it += gridDim.x) {
-        const uint32_t g = heavy[1 + it / HEAVY_SPLIT], j = it % HEAVY_SPLIT;
+        const uint32_t h = it / hp.split, j = it % hp.split;
+        const uint32_t g = heavy[1 + h];
         const uint32_t t0 = task_off[g], cnt = task_off[g + 1] - t0;
-        if (cnt < HEAVY_BIG) continue;
-        const uint32_t lo = (uint32_t)((uint64_t)cnt * j / HEAVY_SPLIT), hi = (uint32_t)((uint64_t)cnt * (j + 1) / HEAVY_SPLIT);
+        if (cnt < hp.big) continue;
+        const uint32_t lo = (uint32_t)((uint64_t)cnt * j / hp.split), hi = (uint32_t)((uint64_t)cnt * (j + 1) / hp.split);
         XYZZ<F> s = cta_sum(partials + t0 + lo, hi - lo, smem);
-        if (threadIdx.x == 0) st_struct(tmp + t0 / HEAVY_SPLIT + j, s);
+        if (threadIdx.x == 0) st_struct(tmp + (hp.by_ordinal ? h * hp.split : t0 / hp.split) + j, s);
         __syncthreads();
     }
 }
 
 template <class F>
 __global__ void __launch_bounds__(MSM_RED_THREADS)
-msm_reduce_heavy_kernel(const uint32_t* __restrict__ heavy, const uint32_t* __restrict__ task_off, const uint32_t* __restrict__ perm,
+msm_reduce_heavy_kernel(const uint32_t* __restrict__ heavy, const uint32_t* __restrict__ task_off, const uint32_t* __restrict__ perm, HeavyPlan hp,
                         const XYZZ<F>* __restrict__ partials, const XYZZ<F>* __restrict__ tmp, XYZZ<F>* __restrict__ bucket_acc) {
     extern __shared__ uint4 smem_raw[];
     XYZZ<F>* smem = reinterpret_cast<XYZZ<F>*>(smem_raw);
@@ -304,7 +314,7 @@ msm_reduce_heavy_kernel(const uint32_t* __restrict__ heavy, const uint32_t* __re
         const uint32_t rk = heavy[1 + h];
         const uint32_t g = perm ? perm[rk] : rk;
         const uint32_t t0 = task_off[rk], cnt = task_off[rk + 1] - t0;
-        XYZZ<F> s = cnt < HEAVY_BIG ? cta_sum(partials + t0, cnt, smem) : cta_sum(tmp + t0 / HEAVY_SPLIT, HEAVY_SPLIT, smem);
+        XYZZ<F> s = cnt < hp.big ? cta_sum(partials + t0, cnt, smem) : cta_sum(tmp + (hp.by_ordinal ? h * hp.split : t0 / hp.split), hp.split, smem);
         if (threadIdx.x == 0) st_struct(bucket_acc + g, s);
         __syncthreads();
     }
@@ -374,37 +384,25 @@ static MsmShape msm_shape(uint64_t n, uint32_t scalar_bits, size_t point_bytes) 
     return sh;
 }
 
-template <class Curve, class F>
-static int32_t msm_run_t(Ctx* c, const void* bases_dev, const void* scalars_dev, uint64_t n, bool mont, void* out_dev, void* wins_ext) {
-    using Fr = typename Curve::Fr;
-    using Pt = XYZZ<F>;
-    if (n >= (1ull << 31)) return fail(c, B2S_ERR_INVALID_ARG, "msm: n = %llu exceeds 2^31 - 1", (unsigned long long)n);
-    Pt* out = reinterpret_cast<Pt*>(out_dev);
-    if (n == 0) {
-        B2S_CUDA(c, cudaMemsetAsync(out, 0, sizeof(Pt), c->stream));
-        return B2S_OK;
-    }
-    constexpr bool is_g1_t = sizeof(F) == sizeof(typename Curve::Fq);
-    MsmShape sh = msm_shape(n, Curve::FrP::BITS, sizeof(Pt));
-    if ((uint64_t)sh.nwin * n >= (1ull << 32)) return fail(c, B2S_ERR_INVALID_ARG, "msm: n * windows exceeds 2^32");
-    // batched-affine halving rounds (msm_affine.cuh); afterwards the points are already in bucket order.
-    // Rounds are worth it when buckets hold several points: R = ceil(log2(points per bucket)) rounds leave <= 2 points
-    // per average bucket for the XYZZ kernel; heavy buckets (skewed scalars) shrink by 2^R as well.
+// ---- bucket sums of an arbitrary bucket structure ---------------------------------------------------------------
+// How many batched-affine rounds pay for T entries in G buckets, and the XYZZ task length after them.
+struct RoundPlan { uint32_t rounds, L; uint64_t max_tasks; bool stage; };
+template <class F>
+static RoundPlan plan_rounds(Ctx* c, uint64_t T, uint32_t G, bool is_g1, uint32_t L_default, bool random_gathers) {
+    RoundPlan rp{0, L_default, T / L_default + G + 1, false};
     uint32_t ba_auto = 0;
-    {
-        const uint64_t per_bucket = ((uint64_t)sh.nwin * n) / sh.G;
-        while ((1ull << ba_auto) < per_bucket) ba_auto++;
-        // a round has a fixed price -- one latency-bound inversion level (~0.7 ms) plus a dozen small launches -- and
-        // saves 4 (G1) / 11 (G2) base multiplications on each of its T / 2^(r+1) additions: keep the rounds that pay
-        const double min_adds = is_g1_t ? 6.0e6 : 2.5e6;
-        uint32_t pays = 0;
-        while (pays < 16 && (double)((uint64_t)sh.nwin * n >> (pays + 1)) > min_adds) pays++;
-        ba_auto = std::min(ba_auto, pays);
-    }
-    uint32_t ba_rounds = env_u32("B2S_MSM_AFFINE_ROUNDS", ba_auto);
-    // scratch of the rounds: two output buffers, the prefix products and the lane totals (bounded by the first round)
-    {
-        const uint64_t t0 = std::min<uint64_t>((uint64_t)sh.nwin * n, ((uint64_t)sh.nwin * n + sh.G) / 2 + 1);
+    const uint64_t per_bucket = G ? T / G : 0;
+    while ((1ull << ba_auto) < per_bucket) ba_auto++;
+    // a round has a fixed price -- one latency-bound inversion level (~0.7 ms) plus a dozen small launches -- and
+    // saves 4 (G1) / 11 (G2) base multiplications on each of its T / 2^(r+1) additions: keep the rounds that pay
+    const double min_adds = is_g1 ? 6.0e6 : 2.5e6;
+    uint32_t pays = 0;
+    while (pays < 16 && (double)(T >> (pays + 1)) > min_adds) pays++;
+    ba_auto = std::min(ba_auto, pays);
+    rp.rounds = env_u32("B2S_MSM_AFFINE_ROUNDS", ba_auto);
+    if (rp.rounds && !getenv("B2S_MSM_AFFINE_ROUNDS")) {
+        // scratch of the rounds: two output buffers, the prefix products and the lane totals (bounded by the first round)
+        const uint64_t t0 = std::min<uint64_t>(T, (T + G) / 2 + 1);
         const uint64_t need = t0 * (sizeof(Affine<F>) * 3 / 2 + sizeof(F)) + t0 / 4;
         size_t free_b = 0, total_b = 0;
         cudaMemGetInfo(&free_b, &total_b);
@@ -416,62 +414,57 @@ static int32_t msm_run_t(Ctx* c, const void* bases_dev, const void* scalars_dev,
             cudaMemPoolGetAttribute(pool, cudaMemPoolAttrUsedMemCurrent, &used);
             pool_held = reserved > used ? reserved - used : 0;
         }
-        if (ba_rounds && need + ((uint64_t)2 << 30) > (uint64_t)free_b + pool_held && !getenv("B2S_MSM_AFFINE_ROUNDS")) ba_rounds = 0;
+        if (need + ((uint64_t)2 << 30) > (uint64_t)free_b + pool_held) rp.rounds = 0;
+        // staged first round (the points of a random-access first round are fetched once and written out as pairs; 2 more
+        // points per output).  OFF by default: measured neutral-to-worse (2^24 uniform G1: pass 2 52.9 -> 43.5 ms but pass 1
+        // 18.3 -> 30.7 ms -- the gather count is the same and pass 1 now also writes 192 B per pair; profiles/r02_experiments.md)
+        const uint64_t need_stage = need + 2 * t0 * sizeof(Affine<F>);
+        rp.stage = rp.rounds && random_gathers && env_u32("B2S_MSM_STAGE", 0) && need_stage + ((uint64_t)4 << 30) <= (uint64_t)free_b + pool_held;
     }
-    if (ba_rounds && !getenv("B2S_MSM_L")) {
+    if (rp.rounds && getenv("B2S_MSM_AFFINE_ROUNDS")) rp.stage = random_gathers && env_u32("B2S_MSM_STAGE", 0);
+    if (rp.rounds && !getenv("B2S_MSM_L")) {
         // what the XYZZ kernel sees after the rounds is 2^-R of the input: cut its tasks accordingly, otherwise the heavy
         // buckets of skewed scalars (a few thousand tasks of ~1000 points) leave most of the machine idle
-        uint64_t t_after = (uint64_t)sh.nwin * n;
-        for (uint32_t r = 0; r < ba_rounds; r++) t_after = std::min<uint64_t>(t_after, (t_after + sh.G) / 2 + 1);
-        sh.L = (uint32_t)std::max<uint64_t>(16, t_after >> 18);
-        sh.max_tasks = t_after / sh.L + sh.G + 1;
+        uint64_t t_after = T;
+        for (uint32_t r = 0; r < rp.rounds; r++) t_after = std::min<uint64_t>(t_after, (t_after + G) / 2 + 1);
+        rp.L = (uint32_t)std::max<uint64_t>(16, t_after >> 18);
+        rp.max_tasks = t_after / rp.L + G + 1;
     }
-    const Fr* scalars = reinterpret_cast<const Fr*>(scalars_dev);
-    const Affine<F>* bases = reinterpret_cast<const Affine<F>*>(bases_dev);
+    return rp;
+}
 
-    const uint32_t MSM_SEG = env_u32("B2S_MSM_SEG", sh.B >= (1u << 16) ? 32u : 16u);
-    const uint32_t ntiles = (sh.G + SCAN_TILE - 1) / SCAN_TILE;
-    DevBuf ibuf, sorted, bucket_acc, partials, segs, wins, tiles, heavy_tmp;
-    B2S_TRY(tiles.alloc(c, (size_t)ntiles * sizeof(Scan3)));
-    B2S_TRY(heavy_tmp.alloc(c, ((size_t)sh.max_tasks / HEAVY_SPLIT + HEAVY_SPLIT + 1) * sizeof(Pt)));
-    // u32 arrays: counts[G] cursor[G] offsets[G+1] task_off[G+1] heavy[G+1]
-    const size_t ints = (size_t)5 * sh.G + 3;
-    B2S_TRY(ibuf.alloc(c, ints * sizeof(uint32_t)));
-    uint32_t* counts = ibuf.as<uint32_t>();
-    uint32_t* cursor = counts + sh.G;
-    uint32_t* offsets = cursor + sh.G;
-    uint32_t* task_off = offsets + sh.G + 1;
-    uint32_t* heavy = task_off + sh.G + 1;
-    B2S_CUDA(c, cudaMemsetAsync(counts, 0, (size_t)2 * sh.G * sizeof(uint32_t), c->stream));
-    B2S_TRY(sorted.alloc(c, (size_t)sh.nwin * n * sizeof(uint32_t)));
-    B2S_TRY(bucket_acc.alloc(c, (size_t)sh.G * sizeof(Pt)));
-    B2S_CUDA(c, cudaMemsetAsync(bucket_acc.p, 0, (size_t)sh.G * sizeof(Pt), c->stream));  // identity = zeros
-    B2S_TRY(partials.alloc(c, (size_t)sh.max_tasks * sizeof(Pt)));
-    const uint32_t segs_per_win = (sh.B + MSM_SEG - 1) / MSM_SEG;
-    B2S_TRY(segs.alloc(c, (size_t)segs_per_win * sh.nwin * sizeof(Pt)));
-    if (sh.nwin > 64) wins_ext = nullptr;   // caller scratch holds 64 window sums; tiny windows take the in-stream path
-    if (getenv("B2S_NO_AUX")) wins_ext = nullptr;   // debugging knob: keep the Horner tail on the main stream
-    if (!wins_ext) B2S_TRY(wins.alloc(c, (size_t)sh.nwin * sizeof(Pt)));
-    Pt* wins_p = wins_ext ? reinterpret_cast<Pt*>(wins_ext) : wins.as<Pt>();
-
-    B2S_LAUNCH(c, msm_count_kernel<Fr>, cdiv(n, 256), 256, 0, scalars, n, mont, sh, counts);
-    const uint32_t* no_perm = nullptr;
-    B2S_LAUNCH(c, msm_scan_tiles_kernel, ntiles, SCAN_THREADS, 0, counts, no_perm, sh, tiles.as<Scan3>());
-    B2S_LAUNCH(c, msm_scan_spine_kernel, 1, 1024, 0, tiles.as<Scan3>(), ntiles, sh, offsets, task_off, heavy);
-    B2S_LAUNCH(c, msm_scan_apply_kernel, ntiles, SCAN_THREADS, 0, counts, no_perm, sh, tiles.as<Scan3>(), offsets, task_off, heavy);
-    B2S_LAUNCH(c, msm_scatter_kernel<Fr>, cdiv(n, 256), 256, 0, scalars, n, mont, sh, offsets, cursor, sorted.as<uint32_t>());
+// bucket_acc[g] = sum of the points bases[sorted[offsets[g] .. offsets[g+1])] (sign in bit 31), for G buckets holding T
+// entries in all.  counts / offsets are the caller's (device); bucket_acc must be zeroed.  Rounds of batched-affine
+// halving first (msm_affine.cuh), then the XYZZ kernel, then the buckets that were cut into several tasks are joined.
+template <class Curve, class F>
+static int32_t bucket_sums_t(Ctx* c, const Affine<F>* bases, const uint32_t* sorted, uint32_t* counts, uint32_t* offsets, uint64_t T, uint32_t G,
+                             const RoundPlan& rp, XYZZ<F>* bucket_acc) {
+    using Pt = XYZZ<F>;
     constexpr bool is_g1 = sizeof(F) == sizeof(typename Curve::Fq);
+    MsmShape sh{};
+    sh.G = G; sh.L = rp.L; sh.max_tasks = rp.max_tasks;
+    const uint32_t ntiles = (G + SCAN_TILE - 1) / SCAN_TILE;
+    const uint32_t* no_perm = nullptr;
+    DevBuf tiles, tbuf, partials, heavy_tmp;
+    B2S_TRY(tiles.alloc(c, (size_t)ntiles * sizeof(Scan3)));
+    B2S_TRY(tbuf.alloc(c, ((size_t)2 * G + 3) * sizeof(uint32_t)));       // task_off[G+1] heavy[G+1]
+    uint32_t* task_off = tbuf.as<uint32_t>();
+    uint32_t* heavy = task_off + G + 1;
+    B2S_TRY(partials.alloc(c, (size_t)sh.max_tasks * sizeof(Pt)));
+    const HeavyPlan hp = heavy_plan(G);
+    B2S_TRY(heavy_tmp.alloc(c, heavy_tmp_slots(hp, G, sh.max_tasks) * sizeof(Pt)));
     const void* acc_bases = bases;
-    const uint32_t* acc_sorted = sorted.as<uint32_t>();
+    const uint32_t* acc_sorted = sorted;
     const uint32_t* acc_offsets = offsets;
-    DevBuf ba_ints, ba_out[2], ba_prefix, ba_tot, ba_bits;
-    if (ba_rounds) {
-        B2S_TRY(ba_ints.alloc(c, ((size_t)2 * sh.G + 1) * sizeof(uint32_t)));
+    const uint32_t* acc_counts = counts;
+    DevBuf ba_ints, ba_out[2], ba_prefix, ba_tot, ba_bits, ba_staged;
+    if (rp.rounds) {
+        B2S_TRY(ba_ints.alloc(c, ((size_t)2 * G + 1) * sizeof(uint32_t)));
         uint32_t* cnt[2] = {counts, ba_ints.as<uint32_t>()};
-        uint32_t* off[2] = {offsets, ba_ints.as<uint32_t>() + sh.G};
-        uint64_t t_in = (uint64_t)sh.nwin * n;
+        uint32_t* off[2] = {offsets, ba_ints.as<uint32_t>() + G};
+        uint64_t t_in = T;
         // outputs of a round: every bucket keeps ceil(count / 2) points -- at most (t_in + G) / 2 and never more than t_in
-        auto round_bound = [&](uint64_t tin) { return std::min<uint64_t>(tin, (tin + sh.G) / 2 + 1); };
+        auto round_bound = [&](uint64_t tin) { return std::min<uint64_t>(tin, (tin + G) / 2 + 1); };
         const uint64_t out_bound0 = round_bound(t_in);
         const uint64_t words_bound0 = out_bound0 / 32 + 2;
         const uint64_t tot_bound = (words_bound0 / BA_KMIN + 2) * 32;
@@ -485,34 +478,36 @@ static int32_t msm_run_t(Ctx* c, const void* bases_dev, const void* scalars_dev,
         B2S_TRY(ba_tot.alloc(c, 2 * tot_bound * sizeof(F)));
         const uint32_t target_units = 4u * 16u * (uint32_t)c->sm_count;   // ~4 units per resident warp, handed out dynamically
         DevBuf ba_ctr;
-        B2S_TRY(ba_ctr.alloc(c, (size_t)2 * ba_rounds * sizeof(uint32_t)));
-        B2S_CUDA(c, cudaMemsetAsync(ba_ctr.p, 0, (size_t)2 * ba_rounds * sizeof(uint32_t), c->stream));
+        B2S_TRY(ba_ctr.alloc(c, (size_t)2 * rp.rounds * sizeof(uint32_t)));
+        B2S_CUDA(c, cudaMemsetAsync(ba_ctr.p, 0, (size_t)2 * rp.rounds * sizeof(uint32_t), c->stream));
         // the two ping-pong output buffers, sized for the rounds that use them (even rounds write [1], odd rounds [0])
         B2S_TRY(ba_out[1].alloc(c, out_bound0 * sizeof(Affine<F>)));
-        if (ba_rounds > 1) B2S_TRY(ba_out[0].alloc(c, round_bound(out_bound0) * sizeof(Affine<F>)));
+        if (rp.stage) B2S_TRY(ba_staged.alloc(c, 2 * out_bound0 * sizeof(Affine<F>)));
+        if (rp.rounds > 1) B2S_TRY(ba_out[0].alloc(c, round_bound(out_bound0) * sizeof(Affine<F>)));
         int cur = 0;
         const void* prev = nullptr;
-        for (uint32_t r = 0; r < ba_rounds; r++) {
+        for (uint32_t r = 0; r < rp.rounds; r++) {
             const int nxt = cur ^ 1;
             const uint64_t out_bound = round_bound(t_in);
             const uint32_t n_words = (uint32_t)(out_bound / 32 + 2);
             const uint32_t rank_tiles = cdiv(n_words, BA_SCAN_TILE);
-            B2S_LAUNCH(c, msm_ba_halve_kernel, cdiv(sh.G, 256), 256, 0, cnt[cur], sh.G, cnt[nxt]);
+            B2S_LAUNCH(c, msm_ba_halve_kernel, cdiv(G, 256), 256, 0, cnt[cur], G, cnt[nxt]);
             B2S_LAUNCH(c, msm_scan_tiles_kernel, ntiles, SCAN_THREADS, 0, cnt[nxt], no_perm, sh, tiles.as<Scan3>());
             B2S_LAUNCH(c, msm_scan_spine_kernel, 1, 1024, 0, tiles.as<Scan3>(), ntiles, sh, off[nxt], task_off, heavy);
             B2S_LAUNCH(c, msm_scan_apply_kernel, ntiles, SCAN_THREADS, 0, cnt[nxt], no_perm, sh, tiles.as<Scan3>(), off[nxt], task_off, heavy);
             B2S_CUDA(c, cudaMemsetAsync(bitmap, 0, (size_t)n_words * sizeof(uint32_t), c->stream));
-            B2S_LAUNCH(c, msm_ba_singles_kernel, cdiv(sh.G, 256), 256, 0, cnt[cur], off[nxt], sh.G, bitmap);
+            B2S_LAUNCH(c, msm_ba_singles_kernel, cdiv(G, 256), 256, 0, cnt[cur], off[nxt], G, bitmap);
             B2S_LAUNCH(c, msm_ba_rank_tiles_kernel, rank_tiles, BA_SCAN_THREADS, 0, bitmap, n_words, rtiles);
             B2S_LAUNCH(c, msm_ba_rank_spine_kernel, 1, 1024, 0, rtiles, rank_tiles);
             B2S_LAUNCH(c, msm_ba_rank_apply_kernel, rank_tiles, BA_SCAN_THREADS, 0, bitmap, n_words, rtiles, wrank);
             BaRoundArgs ra{};
             ra.first = r == 0;
-            ra.bases = bases; ra.sorted = sorted.as<uint32_t>(); ra.prev = prev;
-            ra.bitmap = bitmap; ra.wrank = wrank; ra.t_out = off[nxt] + sh.G;
+            ra.bases = bases; ra.sorted = sorted; ra.prev = prev;
+            ra.bitmap = bitmap; ra.wrank = wrank; ra.t_out = off[nxt] + G;
             ra.target_units = target_units;
             ra.unit_ctr = ba_ctr.as<uint32_t>() + 2 * r;
             ra.prefix = ba_prefix.p; ra.tot = ba_tot.p; ra.inv_scratch = ba_tot.as<F>() + tot_bound; ra.out = ba_out[nxt].p;
+            ra.staged = (r == 0 && rp.stage) ? ba_staged.p : nullptr;
             if (is_g1) B2S_TRY(msm_ba_round_g1(c, ra));
             else B2S_TRY(msm_ba_round_g2(c, ra));
             prev = ba_out[nxt].p;
@@ -522,35 +517,91 @@ static int32_t msm_run_t(Ctx* c, const void* bases_dev, const void* scalars_dev,
         acc_bases = prev;
         acc_sorted = nullptr;
         acc_offsets = off[cur];
+        acc_counts = cnt[cur];
+    } else {
+        // task offsets for the caller's counts (the rounds leave them behind as a by-product of their last scan)
+        B2S_LAUNCH(c, msm_scan_tiles_kernel, ntiles, SCAN_THREADS, 0, counts, no_perm, sh, tiles.as<Scan3>());
+        B2S_LAUNCH(c, msm_scan_spine_kernel, 1, 1024, 0, tiles.as<Scan3>(), ntiles, sh, offsets, task_off, heavy);
+        B2S_LAUNCH(c, msm_scan_apply_kernel, ntiles, SCAN_THREADS, 0, counts, no_perm, sh, tiles.as<Scan3>(), offsets, task_off, heavy);
     }
     // task ranks by decreasing bucket size (skipped after affine rounds, which leave the natural order)
     const uint32_t* perm = nullptr;
     DevBuf perm_buf;
-    if (!ba_rounds && env_u32("B2S_MSM_SIZE_SORT", 1)) {
-        B2S_TRY(perm_buf.alloc(c, ((size_t)sh.G + 2 * SIZE_BINS) * sizeof(uint32_t)));
+    if (!rp.rounds && G >= 1024 && env_u32("B2S_MSM_SIZE_SORT", 1)) {
+        B2S_TRY(perm_buf.alloc(c, ((size_t)G + 2 * SIZE_BINS) * sizeof(uint32_t)));
         uint32_t* pm = perm_buf.as<uint32_t>();
-        uint32_t* hist = pm + sh.G;
+        uint32_t* hist = pm + G;
         uint32_t* binoff = hist + SIZE_BINS;
         uint32_t* none = nullptr;
         B2S_CUDA(c, cudaMemsetAsync(hist, 0, SIZE_BINS * sizeof(uint32_t), c->stream));
-        B2S_LAUNCH(c, msm_size_hist_kernel, cdiv(sh.G, 256), 256, 0, counts, sh.G, hist);
+        B2S_LAUNCH(c, msm_size_hist_kernel, cdiv(G, 256), 256, 0, acc_counts, G, hist);
         B2S_LAUNCH(c, msm_size_scan_kernel, 1, 1024, 0, hist, binoff);
-        B2S_LAUNCH(c, msm_size_scatter_kernel, cdiv(sh.G, 256), 256, 0, counts, sh.G, binoff, hist, pm);
-        B2S_LAUNCH(c, msm_scan_tiles_kernel, ntiles, SCAN_THREADS, 0, counts, (const uint32_t*)pm, sh, tiles.as<Scan3>());
+        B2S_LAUNCH(c, msm_size_scatter_kernel, cdiv(G, 256), 256, 0, acc_counts, G, binoff, hist, pm);
+        B2S_LAUNCH(c, msm_scan_tiles_kernel, ntiles, SCAN_THREADS, 0, acc_counts, (const uint32_t*)pm, sh, tiles.as<Scan3>());
         B2S_LAUNCH(c, msm_scan_spine_kernel, 1, 1024, 0, tiles.as<Scan3>(), ntiles, sh, none, task_off, heavy);
-        B2S_LAUNCH(c, msm_scan_apply_kernel, ntiles, SCAN_THREADS, 0, counts, (const uint32_t*)pm, sh, tiles.as<Scan3>(), none, task_off, heavy);
+        B2S_LAUNCH(c, msm_scan_apply_kernel, ntiles, SCAN_THREADS, 0, acc_counts, (const uint32_t*)pm, sh, tiles.as<Scan3>(), none, task_off, heavy);
         perm = pm;
     }
-    if (is_g1) B2S_TRY(msm_accumulate_g1(c, acc_bases, acc_sorted, acc_offsets, task_off, perm, sh, bucket_acc.p, partials.p));
-    else B2S_TRY(msm_accumulate_g2(c, acc_bases, acc_sorted, acc_offsets, task_off, perm, sh, bucket_acc.p, partials.p));
+    if (is_g1) B2S_TRY(msm_accumulate_g1(c, acc_bases, acc_sorted, acc_offsets, task_off, perm, sh, bucket_acc, partials.p));
+    else B2S_TRY(msm_accumulate_g2(c, acc_bases, acc_sorted, acc_offsets, task_off, perm, sh, bucket_acc, partials.p));
     const size_t red_smem = (size_t)MSM_RED_THREADS * sizeof(Pt);
     B2S_SMEM_ATTR(c, msm_reduce_heavy_kernel<F>, red_smem);
     B2S_SMEM_ATTR(c, msm_reduce_heavy_stage1_kernel<F>, red_smem);
-    B2S_LAUNCH(c, msm_reduce_heavy_stage1_kernel<F>, 4 * c->sm_count, MSM_RED_THREADS, red_smem, heavy, task_off,
+    B2S_LAUNCH(c, msm_reduce_heavy_stage1_kernel<F>, 4 * c->sm_count, MSM_RED_THREADS, red_smem, heavy, task_off, hp,
                partials.as<Pt>(), heavy_tmp.as<Pt>());
-    B2S_LAUNCH(c, msm_reduce_heavy_kernel<F>, 2 * c->sm_count, MSM_RED_THREADS, red_smem, heavy, task_off, perm,
-               partials.as<Pt>(), heavy_tmp.as<Pt>(), bucket_acc.as<Pt>());
-    // bucket reduction: compiled with the multiplication inlined (msm_acc_g1.cu / msm_acc_g2.cu), 2 general additions per bucket
+    B2S_LAUNCH(c, msm_reduce_heavy_kernel<F>, 2 * c->sm_count, MSM_RED_THREADS, red_smem, heavy, task_off, perm, hp,
+               partials.as<Pt>(), heavy_tmp.as<Pt>(), bucket_acc);
+    return B2S_OK;
+}
+
+// ---- the Pippenger pipeline proper ---------------------------------------------------------------------------------
+// index_map (optional): scalar i belongs to base index_map[i] (the multiplicity-aware front end hands over a compacted
+// scalar array); nullptr: base i.
+template <class Curve, class F>
+static int32_t msm_core_t(Ctx* c, const Affine<F>* bases, const typename Curve::Fr* scalars, const uint32_t* index_map, uint64_t n, bool mont,
+                          XYZZ<F>* out, void* wins_ext, bool* used_aux = nullptr) {
+    using Fr = typename Curve::Fr;
+    using Pt = XYZZ<F>;
+    constexpr bool is_g1 = sizeof(F) == sizeof(typename Curve::Fq);
+    if (n == 0) {
+        B2S_CUDA(c, cudaMemsetAsync(out, 0, sizeof(Pt), c->stream));
+        return B2S_OK;
+    }
+    MsmShape sh = msm_shape(n, Curve::FrP::BITS, sizeof(Pt));
+    if ((uint64_t)sh.nwin * n >= (1ull << 32)) return fail(c, B2S_ERR_INVALID_ARG, "msm: n * windows exceeds 2^32");
+    const RoundPlan rp = plan_rounds<F>(c, (uint64_t)sh.nwin * n, sh.G, is_g1, sh.L, true);   // digits of distinct scalars: random gathers
+    sh.L = rp.L; sh.max_tasks = rp.max_tasks;
+    const uint32_t MSM_SEG = env_u32("B2S_MSM_SEG", sh.B >= (1u << 16) ? 32u : 16u);
+    const uint32_t ntiles = (sh.G + SCAN_TILE - 1) / SCAN_TILE;
+    DevBuf ibuf, sorted, bucket_acc, segs, wins, tiles;
+    B2S_TRY(tiles.alloc(c, (size_t)ntiles * sizeof(Scan3)));
+    // u32 arrays: counts[G] cursor[G] offsets[G+1] task_off[G+1] heavy[G+1]
+    const size_t ints = (size_t)5 * sh.G + 3;
+    B2S_TRY(ibuf.alloc(c, ints * sizeof(uint32_t)));
+    uint32_t* counts = ibuf.as<uint32_t>();
+    uint32_t* cursor = counts + sh.G;
+    uint32_t* offsets = cursor + sh.G;
+    uint32_t* task_off = offsets + sh.G + 1;
+    uint32_t* heavy = task_off + sh.G + 1;
+    B2S_CUDA(c, cudaMemsetAsync(counts, 0, (size_t)2 * sh.G * sizeof(uint32_t), c->stream));
+    B2S_TRY(sorted.alloc(c, (size_t)sh.nwin * n * sizeof(uint32_t)));
+    B2S_TRY(bucket_acc.alloc(c, (size_t)sh.G * sizeof(Pt)));
+    B2S_CUDA(c, cudaMemsetAsync(bucket_acc.p, 0, (size_t)sh.G * sizeof(Pt), c->stream));  // identity = zeros
+    const uint32_t segs_per_win = (sh.B + MSM_SEG - 1) / MSM_SEG;
+    B2S_TRY(segs.alloc(c, (size_t)segs_per_win * sh.nwin * sizeof(Pt)));
+    if (sh.nwin > 64) wins_ext = nullptr;   // caller scratch holds 64 window sums; tiny windows take the in-stream path
+    if (getenv("B2S_NO_AUX")) wins_ext = nullptr;   // debugging knob: keep the Horner tail on the main stream
+    if (!wins_ext) B2S_TRY(wins.alloc(c, (size_t)sh.nwin * sizeof(Pt)));
+    Pt* wins_p = wins_ext ? reinterpret_cast<Pt*>(wins_ext) : wins.as<Pt>();
+
+    B2S_LAUNCH(c, msm_count_kernel<Fr>, cdiv(n, 256), 256, 0, scalars, n, mont, sh, counts);
+    const uint32_t* no_perm = nullptr;
+    B2S_LAUNCH(c, msm_scan_tiles_kernel, ntiles, SCAN_THREADS, 0, counts, no_perm, sh, tiles.as<Scan3>());
+    B2S_LAUNCH(c, msm_scan_spine_kernel, 1, 1024, 0, tiles.as<Scan3>(), ntiles, sh, offsets, task_off, heavy);
+    B2S_LAUNCH(c, msm_scan_apply_kernel, ntiles, SCAN_THREADS, 0, counts, no_perm, sh, tiles.as<Scan3>(), offsets, task_off, heavy);
+    B2S_LAUNCH(c, msm_scatter_kernel<Fr>, cdiv(n, 256), 256, 0, scalars, index_map, n, mont, sh, offsets, cursor, sorted.as<uint32_t>());
+    B2S_TRY((bucket_sums_t<Curve, F>(c, bases, sorted.as<uint32_t>(), counts, offsets, (uint64_t)sh.nwin * n, sh.G, rp, bucket_acc.as<Pt>())));
+    // bucket reduction: compiled with the multiplication inlined (msm_acc_g1.cu), 2 general additions per bucket
     if (is_g1) B2S_TRY(msm_bucket_reduce_g1(c, bucket_acc.p, sh, MSM_SEG, segs.p, segs_per_win, wins_p));
     else B2S_TRY(msm_bucket_reduce_g2(c, bucket_acc.p, sh, MSM_SEG, segs.p, segs_per_win, wins_p));
     if (!wins_ext) {
@@ -561,6 +612,180 @@ static int32_t msm_run_t(Ctx* c, const void* bases_dev, const void* scalars_dev,
         B2S_CUDA(c, cudaStreamWaitEvent(c->aux, c->ev_tail, 0));
         B2S_TRY(msm_horner(c, c->aux, is_g1 ? 1 : 2, wins_p, sh, out));
         c->aux_pending = true;
+        if (used_aux) *used_aux = true;
+    }
+    return B2S_OK;
+}
+
+// ---- multiplicity-aware front end -----------------------------------------------------------------------------------
+// Witness vectors repeat values: the reference's own synthetic circuits assign ONE value to every witness
+// (relations/src/sr1cs/mod.rs:306-309), real circuits are full of 0, 1 and a handful of constants.  Pippenger spends
+// ceil(255 / c) additions on every (point, scalar) pair regardless; but  sum_{i : s_i = v} s_i P_i = v * sum_{i : s_i = v} P_i,
+// ONE addition per point plus one scalar multiplication per distinct heavy value.  So, per MSM:
+//   1 sample   1024 scalars to the host; values seen in >= 3 % of the sample become candidates (at most 8; zero scalars are
+//              simply dropped).  Candidates are hints only -- membership is decided by full 256-bit comparison, so the
+//              result is exact whatever the sample looked like;
+//   2 classify every scalar: candidate j -> heavy list j (a bucket structure of <= 8 buckets), anything else -> the REST;
+//   3 heavy    bucket sums of the heavy lists with the same batched-affine rounds + XYZZ kernels (bucket_sums_t);
+//   4 rest     the ordinary pipeline (msm_core_t) over the compacted rest, bases addressed through the index list;
+//   5 finish   out = rest + sum_j v_j * S_j  (four-lane team scalar multiplications, one warp per candidate).
+// Uniform scalars never get past step 1 (one 32 KiB copy and a stream synchronisation, ~0.1 ms).
+static constexpr uint32_t DEDUP_SAMPLES = 1024, DEDUP_MAX = 8;
+struct DedupCand { uint32_t v[DEDUP_MAX][8]; uint32_t k; };   // candidate values in the caller's representation (Montgomery or canonical)
+
+template <class Fr>
+__global__ void msm_sample_kernel(const Fr* __restrict__ scalars, uint64_t n, uint64_t stride, Fr* __restrict__ out) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= DEDUP_SAMPLES) return;
+    const uint64_t i = (uint64_t)t * stride;
+    if (i < n) st_struct(out + t, ld_struct(scalars + i));
+}
+// gid: 0..k-1 heavy list, DEDUP_MAX = rest, DEDUP_MAX + 1 = zero (dropped)
+template <class Fr>
+__device__ __forceinline__ uint32_t dedup_gid(const Fr& s, const DedupCand& cd) {
+    uint32_t nz = 0;
+#pragma unroll
+    for (int j = 0; j < 8; j++) nz |= s.v[j];
+    if (nz == 0) return DEDUP_MAX + 1;
+    for (uint32_t k = 0; k < cd.k; k++) {
+        uint32_t d = 0;
+#pragma unroll
+        for (int j = 0; j < 8; j++) d |= s.v[j] ^ cd.v[k][j];
+        if (d == 0) return k;
+    }
+    return DEDUP_MAX;
+}
+// pass 0: counts[gid]++;  pass 1: lists (heavy: index into sorted at off[gid] + cursor, rest: compacted index + scalar copy)
+template <class Fr, int PASS>
+__global__ void msm_classify_kernel(const Fr* __restrict__ scalars, uint64_t n, DedupCand cd, uint32_t* __restrict__ counts /*DEDUP_MAX + 1*/,
+                                    const uint32_t* __restrict__ off, uint32_t* __restrict__ cursor, uint32_t* __restrict__ heavy_sorted,
+                                    uint32_t* __restrict__ rest_idx, Fr* __restrict__ rest_scalars) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned lane = threadIdx.x & 31;
+    Fr s = Fr::zero();
+    uint32_t gid = DEDUP_MAX + 1;
+    if (i < n) { s = ld_struct(scalars + i); gid = dedup_gid(s, cd); }
+    const unsigned peers = __match_any_sync(0xffffffffu, gid);
+    if (gid > DEDUP_MAX) return;
+    const unsigned leader = (unsigned)(__ffs(peers) - 1);
+    const uint32_t rank = __popc(peers & ((1u << lane) - 1u));
+    if (PASS == 0) {
+        if (lane == leader) atomicAdd(&counts[gid], (uint32_t)__popc(peers));
+    } else {
+        uint32_t base = 0;
+        if (lane == leader) base = atomicAdd(&cursor[gid], (uint32_t)__popc(peers));
+        base = __shfl_sync(peers, base, leader);
+        if (gid < DEDUP_MAX) heavy_sorted[off[gid] + base + rank] = (uint32_t)i;
+        else { rest_idx[base + rank] = (uint32_t)i; st_struct(rest_scalars + base + rank, s); }
+    }
+}
+// out += sum_j v_j * S_j   (one warp per candidate)
+template <class Curve, class F>
+__global__ void __launch_bounds__(32 * DEDUP_MAX)
+msm_heavy_finish_kernel(const XYZZ<F>* __restrict__ sums, DedupCand cd, bool mont, XYZZ<F>* __restrict__ out) {
+    using Fr = typename Curve::Fr;
+    extern __shared__ uint4 fin_smem[];
+    XYZZ<F>* table = reinterpret_cast<XYZZ<F>*>(fin_smem);            // [k][16]
+    XYZZ<F>* res = table + (size_t)DEDUP_MAX * 16;                      // [k]
+    const uint32_t w = threadIdx.x >> 5;
+    if (w < cd.k) {
+        Fr v;
+#pragma unroll
+        for (int j = 0; j < 8; j++) v.v[j] = cd.v[w][j];
+        if (mont) v = v.from_mont();
+        else { v = v.to_mont(); v = v.from_mont(); }                    // canonical input may exceed r: reduce
+        XYZZ<F> r = team_scalar_mul(ld_struct(sums + w), v.v, Fr::N, table + (size_t)w * 16);
+        if ((threadIdx.x & 31) == 0) res[w] = r;
+    }
+    __syncthreads();
+    if (w == 0) {
+        XYZZ<F> acc = ld_plain(out);
+        for (uint32_t j = 0; j < cd.k; j++) team_add(acc, res[j]);
+        if (threadIdx.x == 0) st_struct(out, acc);
+    }
+}
+
+template <class Curve, class F>
+static int32_t msm_run_t(Ctx* c, const void* bases_dev, const void* scalars_dev, uint64_t n, bool mont, void* out_dev, void* wins_ext) {
+    using Fr = typename Curve::Fr;
+    using Pt = XYZZ<F>;
+    constexpr bool is_g1 = sizeof(F) == sizeof(typename Curve::Fq);
+    if (n >= (1ull << 31)) return fail(c, B2S_ERR_INVALID_ARG, "msm: n = %llu exceeds 2^31 - 1", (unsigned long long)n);
+    const Fr* scalars = reinterpret_cast<const Fr*>(scalars_dev);
+    const Affine<F>* bases = reinterpret_cast<const Affine<F>*>(bases_dev);
+    Pt* out = reinterpret_cast<Pt*>(out_dev);
+    DedupCand cd{};
+    if (n >= env_u32("B2S_MSM_DEDUP_MIN", 1u << 16) && env_u32("B2S_MSM_DEDUP", 1)) {
+        // step 1: sample
+        DevBuf sm;
+        B2S_TRY(sm.alloc(c, DEDUP_SAMPLES * sizeof(Fr)));
+        const uint64_t stride = std::max<uint64_t>(1, n / DEDUP_SAMPLES);
+        B2S_LAUNCH(c, msm_sample_kernel<Fr>, cdiv(DEDUP_SAMPLES, 256), 256, 0, scalars, n, stride, sm.as<Fr>());
+        std::vector<uint32_t> hs((size_t)DEDUP_SAMPLES * 8);
+        B2S_CUDA(c, cudaMemcpyAsync(hs.data(), sm.p, hs.size() * 4, cudaMemcpyDeviceToHost, c->stream));
+        B2S_CUDA(c, cudaStreamSynchronize(c->stream));
+        std::map<std::array<uint32_t, 8>, uint32_t> freq;
+        const uint32_t taken = (uint32_t)std::min<uint64_t>(DEDUP_SAMPLES, (n + stride - 1) / stride);
+        for (uint32_t t = 0; t < taken; t++) {
+            std::array<uint32_t, 8> key;
+            memcpy(key.data(), hs.data() + (size_t)t * 8, 32);
+            freq[key]++;
+        }
+        std::vector<std::pair<uint32_t, std::array<uint32_t, 8>>> top;
+        for (auto& kv : freq) {
+            bool zero = true;
+            for (uint32_t w : kv.first) zero = zero && w == 0;
+            if (!zero && kv.second * 100 >= taken * 3) top.push_back({kv.second, kv.first});
+        }
+        std::sort(top.begin(), top.end(), [](auto& a, auto& b) { return a.first > b.first; });
+        for (size_t j = 0; j < top.size() && j < DEDUP_MAX; j++) memcpy(cd.v[cd.k++], top[j].second.data(), 32);
+    }
+    if (cd.k == 0) return msm_core_t<Curve, F>(c, bases, scalars, nullptr, n, mont, out, wins_ext);
+
+    // step 2: classify (count, then lists)
+    DevBuf ints, heavy_sorted, rest_idx, rest_scal, hsums;
+    B2S_TRY(ints.alloc(c, (3 * (DEDUP_MAX + 2)) * sizeof(uint32_t)));          // counts | offsets | cursor
+    uint32_t* counts = ints.as<uint32_t>();
+    uint32_t* offs = counts + DEDUP_MAX + 2;
+    uint32_t* cursor = offs + DEDUP_MAX + 2;
+    B2S_CUDA(c, cudaMemsetAsync(ints.p, 0, ints.bytes, c->stream));
+    B2S_LAUNCH_N(c, "msm_classify_count", (msm_classify_kernel<Fr, 0>), cdiv(n, 256), 256, 0, scalars, n, cd, counts, (const uint32_t*)offs, cursor,
+                 (uint32_t*)nullptr, (uint32_t*)nullptr, (Fr*)nullptr);
+    uint32_t hcounts[DEDUP_MAX + 1];
+    B2S_CUDA(c, cudaMemcpyAsync(hcounts, counts, sizeof(hcounts), cudaMemcpyDeviceToHost, c->stream));
+    B2S_CUDA(c, cudaStreamSynchronize(c->stream));
+    uint64_t n_heavy = 0;
+    uint32_t hoffs[DEDUP_MAX + 2] = {0};
+    for (uint32_t j = 0; j < DEDUP_MAX; j++) { hoffs[j] = (uint32_t)n_heavy; n_heavy += hcounts[j]; }
+    hoffs[DEDUP_MAX] = (uint32_t)n_heavy;
+    const uint64_t n_rest = hcounts[DEDUP_MAX];
+    if (n_heavy * 8 < n) return msm_core_t<Curve, F>(c, bases, scalars, nullptr, n, mont, out, wins_ext);   // the sample misled: not worth it
+    B2S_CUDA(c, cudaMemcpyAsync(offs, hoffs, sizeof(hoffs), cudaMemcpyHostToDevice, c->stream));
+    B2S_TRY(heavy_sorted.alloc(c, std::max<uint64_t>(n_heavy, 1) * sizeof(uint32_t)));
+    B2S_TRY(rest_idx.alloc(c, std::max<uint64_t>(n_rest, 1) * sizeof(uint32_t)));
+    B2S_TRY(rest_scal.alloc(c, std::max<uint64_t>(n_rest, 1) * sizeof(Fr)));
+    B2S_LAUNCH_N(c, "msm_classify_lists", (msm_classify_kernel<Fr, 1>), cdiv(n, 256), 256, 0, scalars, n, cd, counts, (const uint32_t*)offs, cursor,
+                 heavy_sorted.as<uint32_t>(), rest_idx.as<uint32_t>(), rest_scal.as<Fr>());
+    // step 3: heavy bucket sums (<= DEDUP_MAX buckets)
+    B2S_TRY(hsums.alloc(c, DEDUP_MAX * sizeof(Pt)));
+    B2S_CUDA(c, cudaMemsetAsync(hsums.p, 0, DEDUP_MAX * sizeof(Pt), c->stream));
+    {
+        const RoundPlan rp = plan_rounds<F>(c, n_heavy, DEDUP_MAX, is_g1, (uint32_t)std::max<uint64_t>(64, n_heavy >> 18), false);   // lists in index order: the gathers stream
+        B2S_TRY((bucket_sums_t<Curve, F>(c, bases, heavy_sorted.as<uint32_t>(), counts, offs, n_heavy, DEDUP_MAX, rp, hsums.as<Pt>())));
+    }
+    // step 4: the rest through the ordinary pipeline
+    bool used_aux = false;
+    B2S_TRY((msm_core_t<Curve, F>(c, bases, rest_scal.as<Fr>(), rest_idx.as<uint32_t>(), n_rest, mont, out, wins_ext, &used_aux)));
+    // step 5: on the stream that writes `out` (the aux stream when the Horner tail went there; the heavy sums were finished on
+    // the main stream before the event the aux stream waits for)
+    cudaStream_t fs = used_aux ? c->aux : c->stream;
+    const size_t fin_smem = ((size_t)DEDUP_MAX * 16 + DEDUP_MAX) * sizeof(Pt);
+    B2S_SMEM_ATTR(c, (msm_heavy_finish_kernel<Curve, F>), fin_smem);
+    B2S_LAUNCH_SN(c, fs, is_g1 ? "msm_heavy_finish_g1" : "msm_heavy_finish_g2", (msm_heavy_finish_kernel<Curve, F>), 1, 32 * DEDUP_MAX, fin_smem,
+                  (const Pt*)hsums.as<Pt>(), cd, mont, out);
+    if (used_aux) {
+        cudaFreeAsync(hsums.p, c->aux);   // the buffer must outlive the aux-stream kernel: freed in that stream's order
+        hsums.p = nullptr;
     }
     return B2S_OK;
 }

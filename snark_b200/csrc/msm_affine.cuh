@@ -49,12 +49,16 @@ __host__ __device__ constexpr uint32_t ba_slot_bytes(uint32_t n) { return ((((n 
 template <class F>
 struct BaGeom {
     static constexpr uint32_t FE = sizeof(F), PT = sizeof(Affine<F>);
+    static constexpr uint32_t THREADS_ = sizeof(F) > 64 ? 64 : 128;
     static constexpr uint32_t P1_META = 2 * FE, P1_SLOT = ba_slot_bytes(2 * FE + 16);
+    // staged first round (gathers are random): pass 1 fetches the whole points once and writes the pairs out in order
+    static constexpr uint32_t P1S_META = 2 * PT, P1S_SLOT = ba_slot_bytes(2 * PT + 16);
+    static constexpr uint32_t P1S_SMEM = THREADS_ * BA_P1_STAGES * P1S_SLOT;
     // pass 2 stages the two points only; the prefix product travels through registers (one row ahead) so that the slot
     // ring of 16 warps fits an SM: occupancy is what hides the dependent-issue latency of the carry chains (ncu: `wait`)
     static constexpr uint32_t P2_META = 2 * PT, P2_SLOT = ba_slot_bytes(2 * PT + 16);
     // threads per CTA: the G2 slots are twice as big, so half the threads keep three CTAs per SM
-    static constexpr uint32_t THREADS = sizeof(F) > 64 ? 64 : 128;
+    static constexpr uint32_t THREADS = THREADS_;
     static constexpr uint32_t P2_MIN_CTAS = 4;      // register cap of pass 2: 65536 / (THREADS * 4) = 128 (G1) / 256 (G2)
     static constexpr uint32_t P1_SMEM = THREADS * BA_P1_STAGES * P1_SLOT, P2_SMEM = THREADS * BA_P2_STAGES * P2_SLOT;
 };
@@ -134,11 +138,12 @@ __device__ __forceinline__ uint32_t ba_next_unit(uint32_t* ctr, uint32_t lane) {
 
 // descriptor of (row q, this lane): where its inputs are
 struct BaDesc { uint32_t in0, flags; };
-__device__ __forceinline__ BaDesc ba_desc(uint32_t word, uint32_t wr, uint32_t q, uint32_t lane, uint32_t t_out) {
+// dense: the inputs were written as one PAIR per output (staged first round), so output o reads positions 2 o, 2 o + 1
+__device__ __forceinline__ BaDesc ba_desc(uint32_t word, uint32_t wr, uint32_t q, uint32_t lane, uint32_t t_out, uint32_t dense = 0) {
     const uint32_t o = q * 32u + lane;
     BaDesc d;
     d.flags = (o < t_out ? BA_F_VALID : 0u) | (((word >> lane) & 1u) ? BA_F_SINGLE : 0u);
-    d.in0 = 2u * o - (wr + __popc(word & ((1u << lane) - 1u)));
+    d.in0 = 2u * o - (dense ? 0u : wr + __popc(word & ((1u << lane) - 1u)));
     return d;
 }
 
@@ -166,16 +171,23 @@ __device__ __noinline__ F ba_slow_denominator(const Affine<F>* __restrict__ base
 // Software pipeline per lane, time step t:  consume row t-S | issue the copies of row t into the slot just freed |
 // descriptor + sorted indices of row t+1 | bitmap word of row t+2.  A row's operands are in flight during the S-1
 // row computations before its own.
-template <class F, bool FIRST>
+// STAGE (first round only): the lane fetches both whole points (one random access each instead of one here and one in
+// pass 2), and writes the pair -- y already negated where the digit was negative -- to staged[2 o], staged[2 o + 1]; pass 2
+// then streams.
+template <class F, bool FIRST, bool STAGE = false>
 __global__ void __launch_bounds__(BaGeom<F>::THREADS)
 msm_ba_p1_kernel(const Affine<F>* __restrict__ bases, const uint32_t* __restrict__ sorted, const Affine<F>* __restrict__ prev,
                  const uint32_t* __restrict__ bitmap, const uint32_t* __restrict__ wrank, const uint32_t* __restrict__ t_out_p,
-                 uint32_t target_units, uint32_t* __restrict__ unit_ctr, F* __restrict__ prefix, F* __restrict__ tot) {
+                 uint32_t target_units, uint32_t* __restrict__ unit_ctr, F* __restrict__ prefix, F* __restrict__ tot,
+                 Affine<F>* __restrict__ staged) {
     using Gm = BaGeom<F>;
-    constexpr uint32_t S = BA_P1_STAGES, FE = Gm::FE;
+    constexpr uint32_t S = BA_P1_STAGES, FE = Gm::FE, PT = Gm::PT;
+    constexpr uint32_t SLOT = STAGE ? Gm::P1S_SLOT : Gm::P1_SLOT, META = STAGE ? Gm::P1S_META : Gm::P1_META;
+    constexpr uint32_t X2 = STAGE ? PT : FE;      // where the second point's x sits in the slot
+    static_assert(!STAGE || FIRST, "staging is for the gathered first round");
     extern __shared__ uint4 ba_smem[];
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-    const uint32_t smem0 = (uint32_t)__cvta_generic_to_shared(ba_smem) + (warp * S * 32u + lane) * Gm::P1_SLOT;
+    const uint32_t smem0 = (uint32_t)__cvta_generic_to_shared(ba_smem) + (warp * S * 32u + lane) * SLOT;
     const uint32_t t_out = *t_out_p;
     const uint32_t n_rows = (t_out + 31u) >> 5;
     const uint32_t K = ba_rows_per_unit(n_rows, target_units);
@@ -191,17 +203,27 @@ msm_ba_p1_kernel(const Affine<F>* __restrict__ bases, const uint32_t* __restrict
             if (t >= (int32_t)S) {
                 cp_async_wait<(int)S - 1>();
                 const uint32_t i = (uint32_t)t - S;
-                const uint32_t slot = smem0 + (i % S) * 32u * Gm::P1_SLOT;
-                const uint4 meta = lds16(slot + Gm::P1_META);   // e1, e2, in0, flags
+                const uint32_t slot = smem0 + (i % S) * 32u * SLOT;
+                const uint4 meta = lds16(slot + META);   // e1, e2, in0, flags
                 if (meta.w & BA_F_VALID) {
                     const bool single = (meta.w & BA_F_SINGLE) != 0;
                     const uint32_t o = (q0 + i) * 32u + lane;
                     F d = F::one();                              // no partner: the output is a copy
                     if (!single) {
-                        const F x1 = lds_struct<F>(slot), x2 = lds_struct<F>(slot + FE);
+                        const F x1 = lds_struct<F>(slot), x2 = lds_struct<F>(slot + X2);
                         // x = 0 may be the (0,0) encoding of infinity, equal x means doubling or cancellation
                         if (!x1.is_zero() && !x2.is_zero() && x1 != x2) d = x2 - x1;
                         else d = ba_slow_denominator<F, FIRST>(bases, prev, meta.x, meta.y, meta.z, false);
+                    }
+                    if (STAGE) {
+                        Affine<F> p = lds_struct<Affine<F>>(slot);
+                        if (meta.x >> 31) p.y = p.y.neg();
+                        st_struct(staged + 2 * (size_t)o, p);
+                        if (!single) {
+                            p = lds_struct<Affine<F>>(slot + PT);
+                            if (meta.y >> 31) p.y = p.y.neg();
+                            st_struct(staged + 2 * (size_t)o + 1, p);
+                        }
                     }
                     st_struct(prefix + o, prod);
                     prod = prod * d;
@@ -209,16 +231,16 @@ msm_ba_p1_kernel(const Affine<F>* __restrict__ bases, const uint32_t* __restrict
             }
             // -- issue the copies of row t (descriptor from the previous step); its slot was freed just above
             if (t >= 0 && (uint32_t)t < nr) {
-                const uint32_t slot = smem0 + ((uint32_t)t % S) * 32u * Gm::P1_SLOT;
+                const uint32_t slot = smem0 + ((uint32_t)t % S) * 32u * SLOT;
                 if (b_d.flags & BA_F_VALID) {
                     const F* px1 = FIRST ? &bases[b_e1 & 0x7fffffffu].x : &prev[b_d.in0].x;
-                    cp_async_bytes<FE>(slot, px1);
+                    cp_async_bytes<STAGE ? PT : FE>(slot, px1);
                     if (!(b_d.flags & BA_F_SINGLE)) {
                         const F* px2 = FIRST ? &bases[b_e2 & 0x7fffffffu].x : &prev[b_d.in0 + 1].x;
-                        cp_async_bytes<FE>(slot + FE, px2);
+                        cp_async_bytes<STAGE ? PT : FE>(slot + X2, px2);
                     }
                 }
-                sts16(slot + Gm::P1_META, make_uint4(b_e1, b_e2, b_d.in0, b_d.flags));
+                sts16(slot + META, make_uint4(b_e1, b_e2, b_d.in0, b_d.flags));
             }
             cp_async_commit();
             // -- descriptor of row t + 1, its sorted indices
@@ -281,7 +303,7 @@ __global__ void __launch_bounds__(BaGeom<F>::THREADS, BaGeom<F>::P2_MIN_CTAS)
 msm_ba_p2_kernel(const Affine<F>* __restrict__ bases, const uint32_t* __restrict__ sorted, const Affine<F>* __restrict__ prev,
                  const uint32_t* __restrict__ bitmap, const uint32_t* __restrict__ wrank, const uint32_t* __restrict__ t_out_p,
                  uint32_t target_units, uint32_t* __restrict__ unit_ctr, const F* __restrict__ prefix, const F* __restrict__ tot_inv,
-                 Affine<F>* __restrict__ out) {
+                 Affine<F>* __restrict__ out, uint32_t dense) {
     using Gm = BaGeom<F>;
     constexpr uint32_t S = BA_P2_STAGES, FE = Gm::FE, PT = Gm::PT;
     extern __shared__ uint4 ba_smem[];
@@ -358,7 +380,7 @@ msm_ba_p2_kernel(const Affine<F>* __restrict__ bases, const uint32_t* __restrict
             }
             cp_async_commit();
             if (t + 1 >= 0 && (uint32_t)(t + 1) < nr) {
-                b_d = ba_desc(a_word, a_wr, q0 + nr - 1 - (uint32_t)(t + 1), lane, t_out);
+                b_d = ba_desc(a_word, a_wr, q0 + nr - 1 - (uint32_t)(t + 1), lane, t_out, dense);
                 if (FIRST && (b_d.flags & BA_F_VALID)) {
                     b_e1 = sorted[b_d.in0];
                     b_e2 = (b_d.flags & BA_F_SINGLE) ? 0u : sorted[b_d.in0 + 1];
@@ -475,6 +497,7 @@ struct BaRoundArgs {
     void* tot;                    // F[lane totals bound]
     void* inv_scratch;            // F[lane totals bound]
     void* out;                    // Affine<F>[t_out bound]
+    void* staged;                 // first round only, optional: Affine<F>[2 * t_out bound] -- gather once, then stream
 };
 int32_t msm_ba_round_g1(Ctx* c, const BaRoundArgs& a);
 int32_t msm_ba_round_g2(Ctx* c, const BaRoundArgs& a);
@@ -486,27 +509,36 @@ static int32_t msm_ba_round_launch(Ctx* c, const char* l1, const char* li, const
     const Affine<F>* prev = reinterpret_cast<const Affine<F>*>(a.prev);
     F* prefix = reinterpret_cast<F*>(a.prefix);
     F* tot = reinterpret_cast<F*>(a.tot);
-    // persistent grids: four CTAs per SM for both passes (16 warps; pass 2 is register- and shared-memory-bound there)
+    // persistent grids: four CTAs per SM for pass 2 (16 warps; register- and shared-memory-bound there), up to five for pass 1
     const unsigned ctas = 4u * (unsigned)c->sm_count;
-    const unsigned ctas1 = (unsigned)c->sm_count * std::max(1u, std::min(5u, (224u * 1024u) / (Gm::P1_SMEM + 1024u)));   // pass 1 is lighter
-    if (a.first) {
-        B2S_SMEM_ATTR(c, (msm_ba_p1_kernel<F, true>), Gm::P1_SMEM);
-        B2S_SMEM_ATTR(c, (msm_ba_p2_kernel<F, true>), Gm::P2_SMEM);
-        B2S_LAUNCH_N(c, l1, (msm_ba_p1_kernel<F, true>), ctas1, Gm::THREADS, Gm::P1_SMEM, bases, a.sorted, prev, a.bitmap, a.wrank, a.t_out,
-                     a.target_units, a.unit_ctr, prefix, tot);
+    auto fit = [&](uint32_t smem) { return (unsigned)c->sm_count * std::max(1u, std::min(5u, (224u * 1024u) / (smem + 1024u))); };
+    Affine<F>* staged = reinterpret_cast<Affine<F>*>(a.staged);
+    Affine<F>* out = reinterpret_cast<Affine<F>*>(a.out);
+    const bool stage = a.first && staged != nullptr;
+    if (stage) {
+        B2S_SMEM_ATTR(c, (msm_ba_p1_kernel<F, true, true>), Gm::P1S_SMEM);
+        B2S_LAUNCH_N(c, l1, (msm_ba_p1_kernel<F, true, true>), fit(Gm::P1S_SMEM), Gm::THREADS, Gm::P1S_SMEM, bases, a.sorted, prev, a.bitmap, a.wrank,
+                     a.t_out, a.target_units, a.unit_ctr, prefix, tot, staged);
+    } else if (a.first) {
+        B2S_SMEM_ATTR(c, (msm_ba_p1_kernel<F, true, false>), Gm::P1_SMEM);
+        B2S_LAUNCH_N(c, l1, (msm_ba_p1_kernel<F, true, false>), fit(Gm::P1_SMEM), Gm::THREADS, Gm::P1_SMEM, bases, a.sorted, prev, a.bitmap, a.wrank,
+                     a.t_out, a.target_units, a.unit_ctr, prefix, tot, staged);
     } else {
-        B2S_SMEM_ATTR(c, (msm_ba_p1_kernel<F, false>), Gm::P1_SMEM);
-        B2S_SMEM_ATTR(c, (msm_ba_p2_kernel<F, false>), Gm::P2_SMEM);
-        B2S_LAUNCH_N(c, l1, (msm_ba_p1_kernel<F, false>), ctas1, Gm::THREADS, Gm::P1_SMEM, bases, a.sorted, prev, a.bitmap, a.wrank, a.t_out,
-                     a.target_units, a.unit_ctr, prefix, tot);
+        B2S_SMEM_ATTR(c, (msm_ba_p1_kernel<F, false, false>), Gm::P1_SMEM);
+        B2S_LAUNCH_N(c, l1, (msm_ba_p1_kernel<F, false, false>), fit(Gm::P1_SMEM), Gm::THREADS, Gm::P1_SMEM, bases, a.sorted, prev, a.bitmap, a.wrank,
+                     a.t_out, a.target_units, a.unit_ctr, prefix, tot, staged);
     }
     B2S_LAUNCH_N(c, li, msm_ba_inv_kernel<F>, 4 * c->sm_count, 128, 0, tot, a.t_out, a.target_units, reinterpret_cast<F*>(a.inv_scratch));
-    if (a.first)
+    if (a.first && !stage) {
+        B2S_SMEM_ATTR(c, (msm_ba_p2_kernel<F, true>), Gm::P2_SMEM);
         B2S_LAUNCH_N(c, l2, (msm_ba_p2_kernel<F, true>), ctas, Gm::THREADS, Gm::P2_SMEM, bases, a.sorted, prev, a.bitmap, a.wrank, a.t_out,
-                     a.target_units, a.unit_ctr + 1, (const F*)prefix, (const F*)tot, reinterpret_cast<Affine<F>*>(a.out));
-    else
-        B2S_LAUNCH_N(c, l2, (msm_ba_p2_kernel<F, false>), ctas, Gm::THREADS, Gm::P2_SMEM, bases, a.sorted, prev, a.bitmap, a.wrank, a.t_out,
-                     a.target_units, a.unit_ctr + 1, (const F*)prefix, (const F*)tot, reinterpret_cast<Affine<F>*>(a.out));
+                     a.target_units, a.unit_ctr + 1, (const F*)prefix, (const F*)tot, out, 0u);
+    } else {
+        // later rounds read the previous round's output; a staged first round reads its own pairs, two per output
+        B2S_SMEM_ATTR(c, (msm_ba_p2_kernel<F, false>), Gm::P2_SMEM);
+        B2S_LAUNCH_N(c, l2, (msm_ba_p2_kernel<F, false>), ctas, Gm::THREADS, Gm::P2_SMEM, bases, a.sorted, stage ? (const Affine<F>*)staged : prev, a.bitmap,
+                     a.wrank, a.t_out, a.target_units, a.unit_ctr + 1, (const F*)prefix, (const F*)tot, out, stage ? 1u : 0u);
+    }
     return B2S_OK;
 }
 

@@ -19,20 +19,20 @@ def test_dummy_instance_shape():
 
 
 def test_roofline_from_report():
-    d = json.load(open(os.path.join(ROOT, "profiles", "r01_bench_n1_xyzz_only.json")))
-    rep = {k: (1, v * d["steps"]) for k, v in d["kernel_ms_per_step"].items()}
-    rep["msm_accumulate_g1"] = (4 * d["steps"], rep["msm_accumulate_g1"][1])
-    rep["msm_accumulate_g2"] = (d["steps"], rep["msm_accumulate_g2"][1])
-    roof = bench.roofline_from_report(rep, 1 << 24, 1, 24, 6569.6, "measured")
-    assert roof["kernel"].startswith("msm bucket accumulation g1") and roof["traffic"] == 43.77e9
-    assert abs(roof["frac"] - d["roofline"]["frac"]) < 1e-4 and 0.85 < roof["alu"]["frac"] < 1.0
-    # with the batched-affine rounds the three round launches and the XYZZ pass count as one unit per MSM
-    rep2 = dict(rep)
-    rep2["msm_ba_p2_g1"] = (12 * d["steps"], 249.6 * d["steps"])
-    rep2["msm_accumulate_g1"] = (4 * d["steps"], 48.3 * d["steps"])
-    roof2 = bench.roofline_from_report(rep2, 1 << 24, 1, 24, 6569.6, "measured")
-    assert roof2["traffic"] is None and roof2["launch_unit"].startswith("one MSM")
-    assert abs(roof2["avg_launch_ms"] - (249.6 + 48.3) / 4) < 1e-6 and roof2["achieved"] > roof["achieved"]
+    """A per-kernel report of ONE proof (captured on a B200, profiles/r02_bench_n1_mid.json) replayed: the dominant group is
+    the G1 bucket accumulation; its algorithmic bytes are those of all four G1 MSMs of the proof."""
+    d = json.load(open(os.path.join(ROOT, "profiles", "r02_bench_n1_mid.json")))
+    rep = {k: (1, v) for k, v in d["kernel_ms_per_step"].items()}
+    N = 1 << 24
+    roof = bench.roofline_from_report(rep, N, 1, 24, 6569.6, "measured")
+    assert roof["kernel"].startswith("msm bucket accumulation g1") and roof["traffic"] == bench.NCU_TRAFFIC[("g1", 24, 1)]
+    group_ms = sum(v for k, v in d["kernel_ms_per_step"].items() if k in ("msm_accumulate_g1", "msm_ba_p1_g1", "msm_ba_inv_g1", "msm_ba_p2_g1"))
+    pairs = 2 * (N - 1) + (N - 3) + (N - 1)
+    assert abs(roof["avg_launch_ms"] - group_ms) < 1e-6 and abs(roof["achieved"] - pairs * 128 / (group_ms * 1e-3) / 1e9) < 1e-6
+    assert abs(roof["frac"] - roof["achieved"] / 6569.6) < 1e-12 and roof["alu"]["frac"] > 1.0 and set(roof["parts_ms"]) <= set(rep)
+    # sharded: a rank consumes 1 / world of the pairs
+    roof8 = bench.roofline_from_report(rep, N, 8, 24, 6569.6, "measured")
+    assert abs(roof8["algorithmic_bytes_per_launch"] * 8 - roof["algorithmic_bytes_per_launch"]) < 1 and roof8["traffic"] is None
     # a report without MSM kernels still yields a well-formed object
     roof3 = bench.roofline_from_report({"ntt_pass_final<Fr>": (3, 4.5)}, 1 << 24, 1, 24, 6569.6, "measured")
     assert roof3["kernel"] == "ntt_pass_final<Fr>" and roof3["avg_launch_ms"] == 1.5

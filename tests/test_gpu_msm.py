@@ -82,6 +82,34 @@ def test_msm_edge_cases(be, group, affine_rounds):
         assert gpu_msm(be, curve, group, bases, scalars) == omsm.msm_naive(G, bases, scalars), (bases, scalars)
 
 
+@pytest.mark.parametrize("group", [1, 2])
+def test_msm_repeated_scalars(be, group, monkeypatch):
+    """The multiplicity-aware front end (csrc/msm.cu: sample -> candidates -> heavy lists + rest) on inputs small enough for
+    the oracle: all-equal scalars (the reference's DummyCircuit witness, sr1cs/mod.rs:306-309), a few heavy values mixed with
+    zeros and random scalars, heavy values 1 and r - 1, Montgomery and canonical scalar representations."""
+    monkeypatch.setenv("B2S_MSM_DEDUP_MIN", "1")
+    curve = CURVES[be.curve]
+    G = groups(curve)[group - 1]
+    r = curve.r
+    rng = random.Random(41 + group)
+    pool = [G.mul(G.gen, rng.randrange(1, r)) for _ in range(16)] + [None]
+    n = 160
+    bases = [pool[rng.randrange(len(pool))] for _ in range(n)]
+    v1, v2 = rng.randrange(r), rng.randrange(r)
+    mixes = [
+        [v1] * n,
+        [v1 if i % 10 < 7 else (v2 if i % 10 < 9 else rng.randrange(r)) for i in range(n)],
+        [0 if i % 3 == 0 else (1 if i % 3 == 1 else r - 1) for i in range(n)],
+        [v1 if i % 2 else 0 for i in range(n)],
+    ]
+    for scalars in mixes:
+        exp = omsm.msm_pippenger(G, bases, scalars)
+        assert gpu_msm(be, curve, group, bases, scalars) == exp
+        assert gpu_msm(be, curve, group, bases, scalars, mont=False) == exp
+    monkeypatch.setenv("B2S_MSM_AFFINE_ROUNDS", "2")          # the heavy lists through the batched-affine rounds as well
+    assert gpu_msm(be, curve, group, bases, mixes[1]) == omsm.msm_pippenger(G, bases, mixes[1])
+
+
 def test_msm_window_sizes(be, monkeypatch):
     """The result must not depend on the window size c or the task length L."""
     curve = CURVES[be.curve]

@@ -21,7 +21,8 @@ for group in groups:
     ref = {}
     for cfg in os.environ.get("PROBE_CFGS", "0:256,1:256,2:256,3:256,2:512,3:512,2:128").split(","):
         r, k = cfg.split(":")
-        os.environ["B2S_MSM_AFFINE_ROUNDS"] = r; os.environ["B2S_MSM_AFFINE_K"] = k
+        if r == "auto": os.environ.pop("B2S_MSM_AFFINE_ROUNDS", None)
+        else: os.environ["B2S_MSM_AFFINE_ROUNDS"] = r
         for name, s in [kv for kv in (("uniform", sc), ("equal", same)) if kv[0] in os.environ.get("PROBE_KINDS", "uniform,equal").split(",")]:
             out = fn(bases, s, n); be.sync()
             if name not in ref: ref[name] = out
