@@ -218,12 +218,13 @@ def workload_config(args, world):
 # ------------------------------------------------------------------------------------------------
 # roofline of the dominant kernel, from the per-kernel CUDA-event totals of the timed region
 # ------------------------------------------------------------------------------------------------
-# DRAM bytes (dram__bytes_read.sum + dram__bytes_write.sum) of ALL bucket-accumulation launches of one proof at domain 2^24 on
-# one GPU, from the ncu pass of profiles/r02_msm_traffic_summary.txt (the h-query MSM: uniform scalars, five halving rounds +
-# the XYZZ pass) plus the three multiplicity-collapsed MSMs (one streaming round over their heavy list each).  ~20x the
-# algorithmic bytes BY CONSTRUCTION: the bucket method touches every base once per window, and the batched-affine rounds trade
-# multiplications for two more streaming passes per round -- DRAM stays under 45 % busy (same file).
-NCU_TRAFFIC = {("g1", 24, 1): 1.78e11, ("g2", 24, 1): None}
+# DRAM bytes (dram__bytes_read.sum + dram__bytes_write.sum) of the bucket-accumulation launches of the h-query MSM of one
+# proof at domain 2^24 on one GPU (uniform scalars: five halving rounds + the XYZZ pass, 92 % of the group's time), summed over
+# the ncu pass of profiles/r02_msm_traffic_summary.txt; the three multiplicity-collapsed MSMs add one streaming round over
+# their heavy list each (~5 GB apiece, not captured).  ~20x the algorithmic bytes BY CONSTRUCTION: the bucket method touches
+# every base once per window, and the batched-affine rounds trade multiplications for two more streaming passes per round --
+# DRAM stays under 45 % busy (same file).
+NCU_TRAFFIC = {("g1", 24, 1): 1.63e11, ("g2", 24, 1): None}
 
 
 def roofline_from_report(rep, N, world, log_n, peak, peak_src):

@@ -452,13 +452,23 @@ int32_t b2s_profile_report(b2s_ctx* ctx, char* buf, uint64_t cap) {
     B2S_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     std::map<std::string, std::pair<uint64_t, double>> agg;
     const bool verbose = getenv("B2S_PROFILE_VERBOSE") != nullptr;
+    cudaEvent_t prev_end = nullptr;
     for (auto& r : ctx->prof) {
         float ms = 0.f;
         cudaEventElapsedTime(&ms, r.e0, r.e1);
-        if (verbose) fprintf(stderr, "[b2s-profile] %-40s %.3f ms\n", r.name, ms);
+        if (verbose) {
+            // idle time between the end of the previous recorded launch and the start of this one (launch order; kernels of the
+            // aux stream overlap the main stream, so a negative or tiny gap there means "ran concurrently")
+            float gap = 0.f;
+            if (prev_end) cudaEventElapsedTime(&gap, prev_end, r.e0);
+            fprintf(stderr, "[b2s-profile] %-40s %.3f ms  gap %.3f ms\n", r.name, ms, gap);
+            prev_end = r.e1;
+        }
         auto& a = agg[r.name];
         a.first++;
         a.second += ms;
+    }
+    for (auto& r : ctx->prof) {
         cudaEventDestroy(r.e0);
         cudaEventDestroy(r.e1);
     }

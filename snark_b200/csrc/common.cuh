@@ -18,6 +18,7 @@
 namespace b2s {
 
 struct NttPlan;  // ntt.cu
+struct MsmDedupCache;  // msm.cu: classification of a scalar vector, shared by the MSMs of one proof that use the same scalars
 
 struct Ctx {
     int curve = 0;
@@ -41,6 +42,7 @@ struct Ctx {
     struct ProfRec { const char* name; cudaEvent_t e0, e1; };
     std::vector<ProfRec> prof;
     void* fixed_base_tables[2] = {nullptr, nullptr};  // G1 / G2 window tables (setup.cu)
+    MsmDedupCache* dedup_cache = nullptr;             // non-null between msm_dedup_scope_begin / _end (one proof)
 };
 
 inline int32_t fail(Ctx* c, int32_t code, const char* fmt, ...) {
@@ -169,9 +171,18 @@ void ntt_free_plans(Ctx* c);
 // wins_ext == nullptr: the whole MSM runs on c->stream.  Otherwise wins_ext is caller-owned scratch for the
 // window sums (>= 64 XYZZ points, alive until msm_join_tails): the Horner tail is queued on c->aux and the
 // caller must call msm_join_tails(c) before reading out_xyzz_dev on c->stream.
+// pre (optional): bases_dev is a precomputed table [pre->nwin][pre->stride] with row w = 2^(pre->c w) * (row 0), see msm_precompute
+struct MsmPre { uint32_t c, nwin; uint32_t stride; };
 int32_t msm_run(Ctx* c, int group, const void* bases_dev, const void* scalars_dev, uint64_t n, bool scalars_mont,
-                void* out_xyzz_dev, void* wins_ext = nullptr);
+                void* out_xyzz_dev, void* wins_ext = nullptr, const MsmPre* pre = nullptr);
+// table[w * n + i] = 2^(c w) bases[i] (affine), w < nwin; picks c / nwin for n points itself and reports them in *pre
+int32_t msm_precompute(Ctx* c, int group, const void* bases_dev, uint64_t n, void* table_dev, MsmPre* pre);
+uint32_t msm_precompute_windows(Ctx* c, uint64_t n, uint32_t* c_out);
 int32_t msm_join_tails(Ctx* c);
+// a, b_g1 and b_g2 of a proof are MSMs over the SAME scalar vector: inside a scope the multiplicity-aware front end
+// classifies a (pointer, length) pair once and the following MSMs reuse the lists (no second sample / count round trip)
+void msm_dedup_scope_begin(Ctx* c);
+void msm_dedup_scope_end(Ctx* c);
 int32_t scan_counts(Ctx* c, const uint32_t* counts, uint32_t n, uint32_t L, uint32_t* offsets, uint32_t* task_off);
 int32_t fixed_base_run(Ctx* c, int group, const void* scalars_dev, uint64_t n, bool mont, void* out_dev);
 int32_t group_sum_to_affine(Ctx* c, int group, const void* xyzz_dev, uint32_t count, void* out_affine_dev);

@@ -136,6 +136,22 @@ int32_t pk_upload(Ctx* c, const b2s_pk_desc* d, int32_t mem, b2s_pk** out) {
         B2S_TRY(copy_query(c, pk->b_g2_query, d->b_g2_query, d->b2_len, g2, mem, nullptr, pk->b2_ext ? d->delta_g2 : nullptr, kind));
         B2S_TRY(copy_query(c, pk->h_query, d->h_query, d->h_len, g1, mem, nullptr, nullptr, kind));
         B2S_TRY(copy_query(c, pk->l_query, d->l_query, d->l_len, g1, mem, nullptr, nullptr, kind));
+        // Fixed-base window table for the h query: its scalars (the quotient polynomial) are never repeated values, so this is
+        // the MSM that always pays the full Pippenger price; the other queries run over the witness, where the multiplicity-aware
+        // front end usually leaves little.  13 x the query (18 GiB at 2^24): only when it fits comfortably.
+        {
+            const char* env = getenv("B2S_PK_PRECOMP");
+            const uint64_t min_n = getenv("B2S_PK_PRECOMP_MIN") ? strtoull(getenv("B2S_PK_PRECOMP_MIN"), nullptr, 10) : (1ull << 18);
+            uint32_t cc = 0;
+            const uint32_t nw = msm_precompute_windows(c, d->h_len, &cc);
+            size_t free_b = 0, total_b = 0;
+            cudaMemGetInfo(&free_b, &total_b);
+            const uint64_t need = (uint64_t)nw * d->h_len * g1;
+            if (!(env && env[0] == '0') && d->h_len >= min_n && (uint64_t)nw * d->h_len < (1ull << 31) && need * 4 < (uint64_t)free_b) {
+                B2S_TRY(pk->h_table.alloc(c, need));
+                B2S_TRY(msm_precompute(c, 1, pk->h_query.p, d->h_len, pk->h_table.p, &pk->h_pre));
+            }
+        }
         B2S_CUDA(c, cudaStreamSynchronize(c->stream));
         return B2S_OK;
     };
@@ -202,7 +218,9 @@ static int32_t shard_t(Ctx* c, const b2s_pk* pk, const b2s_r1cs* m, const void* 
     // runs side by side with the four MSMs that only need z; the h-query MSM joins them.  The ctx's launch stream is swapped
     // for the duration of the enqueue (everything below the C ABI launches and allocates on c->stream).
     const void* h_shard = nullptr;
-    const bool fork = !getenv("B2S_NO_SIDE_STREAM");
+    // OFF by default: measured no gain at domain 2^24 (both sides are fmaheavy-bound, the transforms just run slower next to
+    // the MSM kernels: 208 vs 204 ms per proof) and the host-buffer path got slower; B2S_SIDE_STREAM=1 enables it
+    const bool fork = getenv("B2S_SIDE_STREAM") != nullptr;
     struct SideGuard {   // an error return must not leave work in flight on the side stream over buffers being released
         Ctx* c; cudaStream_t main; bool active;
         ~SideGuard() { if (active) { c->stream = main; cudaStreamSynchronize(c->side); } }
@@ -219,6 +237,12 @@ static int32_t shard_t(Ctx* c, const b2s_pk* pk, const b2s_r1cs* m, const void* 
     }
     // the MSMs that only need z (their Horner tails run on the aux stream under the following work); G2 first because its
     // tail is the longest
+    // a, b_g1, b_g2 (and l, when its range coincides) run over the same scalars: classify them once (msm.cu)
+    struct DedupScope {
+        Ctx* c;
+        explicit DedupScope(Ctx* ctx) : c(ctx) { msm_dedup_scope_begin(c); }
+        ~DedupScope() { msm_dedup_scope_end(c); }
+    } dedup_scope(c);
     B2S_TRY(msm_run(c, 2, pk->b_g2_query.p, zd + pk->b2_off, pk->b2_len + pk->b2_ext, true, g2_out, w2));
     B2S_TRY(msm_run(c, 1, pk->a_query.p, zd + pk->a_off, pk->a_len + pk->a_ext, true, g1 + 2, w1 + 2 * 64));
     B2S_TRY(msm_run(c, 1, pk->b_g1_query.p, zd + pk->b1_off, pk->b1_len + pk->b1_ext, true, g1 + 3, w1 + 3 * 64));
@@ -229,7 +253,8 @@ static int32_t shard_t(Ctx* c, const b2s_pk* pk, const b2s_r1cs* m, const void* 
     } else {
         B2S_TRY(hs->get(c, pk, m, zd, &h_shard));
     }
-    B2S_TRY(msm_run(c, 1, pk->h_query.p, h_shard, pk->h_len, true, g1 + 0, w1 + 0 * 64));
+    if (pk->h_table.p) B2S_TRY(msm_run(c, 1, pk->h_table.p, h_shard, pk->h_len, true, g1 + 0, w1 + 0 * 64, &pk->h_pre));
+    else B2S_TRY(msm_run(c, 1, pk->h_query.p, h_shard, pk->h_len, true, g1 + 0, w1 + 0 * 64));
     B2S_TRY(msm_join_tails(c));
     return B2S_OK;
 }

@@ -84,7 +84,7 @@ __global__ void msm_count_kernel(const Fr* __restrict__ scalars, uint64_t n, boo
     load_scalar(it, scalars, i, mont);
     for (uint32_t w = 0; w < sh.nwin; w++) {
         const int32_t d = it.next(w, sh.c, sh.nwin);
-        const uint32_t key = d != 0 ? w * sh.B + (uint32_t)(d < 0 ? -d : d) - 1 : 0xffffffffu;
+        const uint32_t key = d != 0 ? (sh.pre_stride ? 0u : w * sh.B) + (uint32_t)(d < 0 ? -d : d) - 1 : 0xffffffffu;
         const unsigned peers = __match_any_sync(active, key);
         if (key != 0xffffffffu && lane == (unsigned)(__ffs(peers) - 1)) atomicAdd(&counts[key], (uint32_t)__popc(peers));
     }
@@ -258,7 +258,7 @@ __global__ void msm_scatter_kernel(const Fr* __restrict__ scalars, const uint32_
     const uint32_t base_idx = index_map ? index_map[i] : (uint32_t)i;
     for (uint32_t w = 0; w < sh.nwin; w++) {
         const int32_t d = it.next(w, sh.c, sh.nwin);
-        const uint32_t key = d != 0 ? w * sh.B + (uint32_t)(d < 0 ? -d : d) - 1 : 0xffffffffu;
+        const uint32_t key = d != 0 ? (sh.pre_stride ? 0u : w * sh.B) + (uint32_t)(d < 0 ? -d : d) - 1 : 0xffffffffu;
         const unsigned peers = __match_any_sync(active, key);
         const unsigned leader = (unsigned)(__ffs(peers) - 1);
         uint32_t base = 0;
@@ -266,7 +266,7 @@ __global__ void msm_scatter_kernel(const Fr* __restrict__ scalars, const uint32_
         base = __shfl_sync(peers, base, leader);
         if (key != 0xffffffffu) {
             const uint32_t rank = __popc(peers & ((1u << lane) - 1u));
-            sorted[offsets[key] + base + rank] = base_idx | (d < 0 ? 0x80000000u : 0u);
+            sorted[offsets[key] + base + rank] = (base_idx + w * sh.pre_stride) | (d < 0 ? 0x80000000u : 0u);
         }
     }
 }
@@ -351,8 +351,15 @@ static uint32_t env_u32(const char* name, uint32_t dflt) {
 // Window size: minimise  n * nwin  (bucket accumulation, mixed additions)  +  nwin * 2^(c-1) * 4.7
 // (bucket reduction: two general additions per bucket at ~1.4x the cost of a mixed one, plus the
 // per-segment double-and-add), subject to the bucket array staying under 4 GiB.
-static MsmShape msm_shape(uint64_t n, uint32_t scalar_bits, size_t point_bytes) {
+static MsmShape msm_shape(uint64_t n, uint32_t scalar_bits, size_t point_bytes, const MsmPre* pre = nullptr) {
     MsmShape sh{};
+    if (pre) {      // the table fixes c; all windows share one bucket set
+        sh.c = pre->c; sh.nwin = pre->nwin; sh.B = 1u << (pre->c - 1); sh.G = sh.B; sh.pre_stride = pre->stride;
+        const uint64_t t_upper = (uint64_t)sh.nwin * n;
+        sh.L = (uint32_t)std::max<uint64_t>(64, t_upper >> 18);
+        sh.max_tasks = t_upper / sh.L + sh.G + 1;
+        return sh;
+    }
     auto nwin_of = [&](uint32_t c) {
         uint32_t nw = (scalar_bits + c - 1) / c;
         // the last window keeps the recoding carry: it must fit in 2^(c-1) buckets
@@ -459,9 +466,13 @@ static int32_t bucket_sums_t(Ctx* c, const Affine<F>* bases, const uint32_t* sor
     const uint32_t* acc_counts = counts;
     DevBuf ba_ints, ba_out[2], ba_prefix, ba_tot, ba_bits, ba_staged;
     if (rp.rounds) {
-        B2S_TRY(ba_ints.alloc(c, ((size_t)2 * G + 1) * sizeof(uint32_t)));
-        uint32_t* cnt[2] = {counts, ba_ints.as<uint32_t>()};
-        uint32_t* off[2] = {offsets, ba_ints.as<uint32_t>() + G};
+        // two internal (counts, offsets) pairs: the caller's arrays are only READ (round 0), so a bucket structure can be
+        // shared by several calls (the heavy lists of a, b_g1, b_g2 of one proof)
+        B2S_TRY(ba_ints.alloc(c, ((size_t)4 * G + 2) * sizeof(uint32_t)));
+        uint32_t* pp_cnt[2] = {ba_ints.as<uint32_t>(), ba_ints.as<uint32_t>() + 2 * G + 1};
+        uint32_t* pp_off[2] = {pp_cnt[0] + G, pp_cnt[1] + G};
+        const uint32_t* cnt_in = counts;
+        const uint32_t* off_in = offsets;
         uint64_t t_in = T;
         // outputs of a round: every bucket keeps ceil(count / 2) points -- at most (t_in + G) / 2 and never more than t_in
         auto round_bound = [&](uint64_t tin) { return std::min<uint64_t>(tin, (tin + G) / 2 + 1); };
@@ -484,40 +495,43 @@ static int32_t bucket_sums_t(Ctx* c, const Affine<F>* bases, const uint32_t* sor
         B2S_TRY(ba_out[1].alloc(c, out_bound0 * sizeof(Affine<F>)));
         if (rp.stage) B2S_TRY(ba_staged.alloc(c, 2 * out_bound0 * sizeof(Affine<F>)));
         if (rp.rounds > 1) B2S_TRY(ba_out[0].alloc(c, round_bound(out_bound0) * sizeof(Affine<F>)));
-        int cur = 0;
         const void* prev = nullptr;
         for (uint32_t r = 0; r < rp.rounds; r++) {
-            const int nxt = cur ^ 1;
+            const int nxt = (int)(r & 1u);
+            uint32_t* cnt_out = pp_cnt[nxt];
+            uint32_t* off_out = pp_off[nxt];
             const uint64_t out_bound = round_bound(t_in);
             const uint32_t n_words = (uint32_t)(out_bound / 32 + 2);
             const uint32_t rank_tiles = cdiv(n_words, BA_SCAN_TILE);
-            B2S_LAUNCH(c, msm_ba_halve_kernel, cdiv(G, 256), 256, 0, cnt[cur], G, cnt[nxt]);
-            B2S_LAUNCH(c, msm_scan_tiles_kernel, ntiles, SCAN_THREADS, 0, cnt[nxt], no_perm, sh, tiles.as<Scan3>());
-            B2S_LAUNCH(c, msm_scan_spine_kernel, 1, 1024, 0, tiles.as<Scan3>(), ntiles, sh, off[nxt], task_off, heavy);
-            B2S_LAUNCH(c, msm_scan_apply_kernel, ntiles, SCAN_THREADS, 0, cnt[nxt], no_perm, sh, tiles.as<Scan3>(), off[nxt], task_off, heavy);
+            B2S_LAUNCH(c, msm_ba_halve_kernel, cdiv(G, 256), 256, 0, cnt_in, G, cnt_out);
+            B2S_LAUNCH(c, msm_scan_tiles_kernel, ntiles, SCAN_THREADS, 0, (const uint32_t*)cnt_out, no_perm, sh, tiles.as<Scan3>());
+            B2S_LAUNCH(c, msm_scan_spine_kernel, 1, 1024, 0, tiles.as<Scan3>(), ntiles, sh, off_out, task_off, heavy);
+            B2S_LAUNCH(c, msm_scan_apply_kernel, ntiles, SCAN_THREADS, 0, (const uint32_t*)cnt_out, no_perm, sh, tiles.as<Scan3>(), off_out, task_off, heavy);
             B2S_CUDA(c, cudaMemsetAsync(bitmap, 0, (size_t)n_words * sizeof(uint32_t), c->stream));
-            B2S_LAUNCH(c, msm_ba_singles_kernel, cdiv(G, 256), 256, 0, cnt[cur], off[nxt], G, bitmap);
+            B2S_LAUNCH(c, msm_ba_singles_kernel, cdiv(G, 256), 256, 0, cnt_in, (const uint32_t*)off_out, G, bitmap);
             B2S_LAUNCH(c, msm_ba_rank_tiles_kernel, rank_tiles, BA_SCAN_THREADS, 0, bitmap, n_words, rtiles);
             B2S_LAUNCH(c, msm_ba_rank_spine_kernel, 1, 1024, 0, rtiles, rank_tiles);
             B2S_LAUNCH(c, msm_ba_rank_apply_kernel, rank_tiles, BA_SCAN_THREADS, 0, bitmap, n_words, rtiles, wrank);
             BaRoundArgs ra{};
             ra.first = r == 0;
             ra.bases = bases; ra.sorted = sorted; ra.prev = prev;
-            ra.bitmap = bitmap; ra.wrank = wrank; ra.t_out = off[nxt] + G;
+            ra.bitmap = bitmap; ra.wrank = wrank; ra.t_out = off_out + G;
             ra.target_units = target_units;
             ra.unit_ctr = ba_ctr.as<uint32_t>() + 2 * r;
-            ra.prefix = ba_prefix.p; ra.tot = ba_tot.p; ra.inv_scratch = ba_tot.as<F>() + tot_bound; ra.out = ba_out[nxt].p;
+            ra.prefix = ba_prefix.p; ra.tot = ba_tot.p; ra.inv_scratch = ba_tot.as<F>() + tot_bound; ra.out = ba_out[nxt ^ 1].p;   // even rounds write [1], odd rounds [0]
             ra.staged = (r == 0 && rp.stage) ? ba_staged.p : nullptr;
             if (is_g1) B2S_TRY(msm_ba_round_g1(c, ra));
             else B2S_TRY(msm_ba_round_g2(c, ra));
-            prev = ba_out[nxt].p;
+            prev = ba_out[nxt ^ 1].p;
             t_in = out_bound;
-            cur = nxt;
+            cnt_in = cnt_out;
+            off_in = off_out;
         }
+        (void)off_in;
         acc_bases = prev;
         acc_sorted = nullptr;
-        acc_offsets = off[cur];
-        acc_counts = cnt[cur];
+        acc_offsets = pp_off[(rp.rounds - 1) & 1u];
+        acc_counts = pp_cnt[(rp.rounds - 1) & 1u];
     } else {
         // task offsets for the caller's counts (the rounds leave them behind as a by-product of their last scan)
         B2S_LAUNCH(c, msm_scan_tiles_kernel, ntiles, SCAN_THREADS, 0, counts, no_perm, sh, tiles.as<Scan3>());
@@ -559,7 +573,7 @@ static int32_t bucket_sums_t(Ctx* c, const Affine<F>* bases, const uint32_t* sor
 // scalar array); nullptr: base i.
 template <class Curve, class F>
 static int32_t msm_core_t(Ctx* c, const Affine<F>* bases, const typename Curve::Fr* scalars, const uint32_t* index_map, uint64_t n, bool mont,
-                          XYZZ<F>* out, void* wins_ext, bool* used_aux = nullptr) {
+                          XYZZ<F>* out, void* wins_ext, bool* used_aux = nullptr, const MsmPre* pre = nullptr) {
     using Fr = typename Curve::Fr;
     using Pt = XYZZ<F>;
     constexpr bool is_g1 = sizeof(F) == sizeof(typename Curve::Fq);
@@ -567,8 +581,9 @@ static int32_t msm_core_t(Ctx* c, const Affine<F>* bases, const typename Curve::
         B2S_CUDA(c, cudaMemsetAsync(out, 0, sizeof(Pt), c->stream));
         return B2S_OK;
     }
-    MsmShape sh = msm_shape(n, Curve::FrP::BITS, sizeof(Pt));
+    MsmShape sh = msm_shape(n, Curve::FrP::BITS, sizeof(Pt), pre);
     if ((uint64_t)sh.nwin * n >= (1ull << 32)) return fail(c, B2S_ERR_INVALID_ARG, "msm: n * windows exceeds 2^32");
+    if (pre && (uint64_t)pre->nwin * pre->stride >= (1ull << 31)) return fail(c, B2S_ERR_INVALID_ARG, "msm: precomputed table exceeds 2^31 points");
     const RoundPlan rp = plan_rounds<F>(c, (uint64_t)sh.nwin * n, sh.G, is_g1, sh.L, true);   // digits of distinct scalars: random gathers
     sh.L = rp.L; sh.max_tasks = rp.max_tasks;
     const uint32_t MSM_SEG = env_u32("B2S_MSM_SEG", sh.B >= (1u << 16) ? 32u : 16u);
@@ -588,7 +603,10 @@ static int32_t msm_core_t(Ctx* c, const Affine<F>* bases, const typename Curve::
     B2S_TRY(bucket_acc.alloc(c, (size_t)sh.G * sizeof(Pt)));
     B2S_CUDA(c, cudaMemsetAsync(bucket_acc.p, 0, (size_t)sh.G * sizeof(Pt), c->stream));  // identity = zeros
     const uint32_t segs_per_win = (sh.B + MSM_SEG - 1) / MSM_SEG;
-    B2S_TRY(segs.alloc(c, (size_t)segs_per_win * sh.nwin * sizeof(Pt)));
+    // what the bucket reduction and the Horner tail see: nwin windows of B buckets, or ONE with a precomputed table
+    MsmShape sh_red = sh;
+    if (pre) sh_red.nwin = 1;
+    B2S_TRY(segs.alloc(c, (size_t)segs_per_win * sh_red.nwin * sizeof(Pt)));
     if (sh.nwin > 64) wins_ext = nullptr;   // caller scratch holds 64 window sums; tiny windows take the in-stream path
     if (getenv("B2S_NO_AUX")) wins_ext = nullptr;   // debugging knob: keep the Horner tail on the main stream
     if (!wins_ext) B2S_TRY(wins.alloc(c, (size_t)sh.nwin * sizeof(Pt)));
@@ -602,15 +620,15 @@ static int32_t msm_core_t(Ctx* c, const Affine<F>* bases, const typename Curve::
     B2S_LAUNCH(c, msm_scatter_kernel<Fr>, cdiv(n, 256), 256, 0, scalars, index_map, n, mont, sh, offsets, cursor, sorted.as<uint32_t>());
     B2S_TRY((bucket_sums_t<Curve, F>(c, bases, sorted.as<uint32_t>(), counts, offsets, (uint64_t)sh.nwin * n, sh.G, rp, bucket_acc.as<Pt>())));
     // bucket reduction: compiled with the multiplication inlined (msm_acc_g1.cu), 2 general additions per bucket
-    if (is_g1) B2S_TRY(msm_bucket_reduce_g1(c, bucket_acc.p, sh, MSM_SEG, segs.p, segs_per_win, wins_p));
-    else B2S_TRY(msm_bucket_reduce_g2(c, bucket_acc.p, sh, MSM_SEG, segs.p, segs_per_win, wins_p));
+    if (is_g1) B2S_TRY(msm_bucket_reduce_g1(c, bucket_acc.p, sh_red, MSM_SEG, segs.p, segs_per_win, wins_p));
+    else B2S_TRY(msm_bucket_reduce_g2(c, bucket_acc.p, sh_red, MSM_SEG, segs.p, segs_per_win, wins_p));
     if (!wins_ext) {
-        B2S_TRY(msm_horner(c, c->stream, is_g1 ? 1 : 2, wins_p, sh, out));
+        B2S_TRY(msm_horner(c, c->stream, is_g1 ? 1 : 2, wins_p, sh_red, out));
     } else {
         // tail on the aux stream: it only needs the window sums, the main stream goes on with the next MSM
         B2S_CUDA(c, cudaEventRecord(c->ev_tail, c->stream));
         B2S_CUDA(c, cudaStreamWaitEvent(c->aux, c->ev_tail, 0));
-        B2S_TRY(msm_horner(c, c->aux, is_g1 ? 1 : 2, wins_p, sh, out));
+        B2S_TRY(msm_horner(c, c->aux, is_g1 ? 1 : 2, wins_p, sh_red, out));
         c->aux_pending = true;
         if (used_aux) *used_aux = true;
     }
@@ -705,8 +723,27 @@ msm_heavy_finish_kernel(const XYZZ<F>* __restrict__ sums, DedupCand cd, bool mon
     }
 }
 
+}  // namespace b2s
+struct b2s::MsmDedupCache {
+    bool valid = false;
+    const void* scalars = nullptr;
+    uint64_t n = 0, n_heavy = 0, n_rest = 0;
+    bool mont = false;
+    DedupCand cd{};
+    DevBuf ints, heavy_sorted, rest_idx, rest_scal;
+};
+namespace b2s {
+void msm_dedup_scope_begin(Ctx* c) {
+    if (!c->dedup_cache) c->dedup_cache = new MsmDedupCache();
+}
+void msm_dedup_scope_end(Ctx* c) {
+    delete c->dedup_cache;      // DevBufs go back to the pool in stream order
+    c->dedup_cache = nullptr;
+}
+
 template <class Curve, class F>
-static int32_t msm_run_t(Ctx* c, const void* bases_dev, const void* scalars_dev, uint64_t n, bool mont, void* out_dev, void* wins_ext) {
+static int32_t msm_run_t(Ctx* c, const void* bases_dev, const void* scalars_dev, uint64_t n, bool mont, void* out_dev, void* wins_ext,
+                         const MsmPre* pre) {
     using Fr = typename Curve::Fr;
     using Pt = XYZZ<F>;
     constexpr bool is_g1 = sizeof(F) == sizeof(typename Curve::Fq);
@@ -714,58 +751,81 @@ static int32_t msm_run_t(Ctx* c, const void* bases_dev, const void* scalars_dev,
     const Fr* scalars = reinterpret_cast<const Fr*>(scalars_dev);
     const Affine<F>* bases = reinterpret_cast<const Affine<F>*>(bases_dev);
     Pt* out = reinterpret_cast<Pt*>(out_dev);
-    DedupCand cd{};
-    if (n >= env_u32("B2S_MSM_DEDUP_MIN", 1u << 16) && env_u32("B2S_MSM_DEDUP", 1)) {
-        // step 1: sample
-        DevBuf sm;
-        B2S_TRY(sm.alloc(c, DEDUP_SAMPLES * sizeof(Fr)));
-        const uint64_t stride = std::max<uint64_t>(1, n / DEDUP_SAMPLES);
-        B2S_LAUNCH(c, msm_sample_kernel<Fr>, cdiv(DEDUP_SAMPLES, 256), 256, 0, scalars, n, stride, sm.as<Fr>());
-        std::vector<uint32_t> hs((size_t)DEDUP_SAMPLES * 8);
-        B2S_CUDA(c, cudaMemcpyAsync(hs.data(), sm.p, hs.size() * 4, cudaMemcpyDeviceToHost, c->stream));
-        B2S_CUDA(c, cudaStreamSynchronize(c->stream));
-        std::map<std::array<uint32_t, 8>, uint32_t> freq;
-        const uint32_t taken = (uint32_t)std::min<uint64_t>(DEDUP_SAMPLES, (n + stride - 1) / stride);
-        for (uint32_t t = 0; t < taken; t++) {
-            std::array<uint32_t, 8> key;
-            memcpy(key.data(), hs.data() + (size_t)t * 8, 32);
-            freq[key]++;
+    // classification of this scalar vector: from the proof's cache when an earlier MSM of the same proof used the same one
+    MsmDedupCache local;
+    MsmDedupCache* dc = c->dedup_cache ? c->dedup_cache : &local;
+    const bool hit = dc->valid && dc->scalars == scalars_dev && dc->n == n && dc->mont == mont;
+    if (!hit) {
+        dc->valid = false;
+        dc->cd = DedupCand{};
+        if (n >= env_u32("B2S_MSM_DEDUP_MIN", 1u << 16) && env_u32("B2S_MSM_DEDUP", 1)) {
+            // step 1: sample
+            DevBuf sm;
+            B2S_TRY(sm.alloc(c, DEDUP_SAMPLES * sizeof(Fr)));
+            const uint64_t stride = std::max<uint64_t>(1, n / DEDUP_SAMPLES);
+            B2S_LAUNCH(c, msm_sample_kernel<Fr>, cdiv(DEDUP_SAMPLES, 256), 256, 0, scalars, n, stride, sm.as<Fr>());
+            std::vector<uint32_t> hs((size_t)DEDUP_SAMPLES * 8);
+            B2S_CUDA(c, cudaMemcpyAsync(hs.data(), sm.p, hs.size() * 4, cudaMemcpyDeviceToHost, c->stream));
+            B2S_CUDA(c, cudaStreamSynchronize(c->stream));
+            std::map<std::array<uint32_t, 8>, uint32_t> freq;
+            const uint32_t taken = (uint32_t)std::min<uint64_t>(DEDUP_SAMPLES, (n + stride - 1) / stride);
+            for (uint32_t t = 0; t < taken; t++) {
+                std::array<uint32_t, 8> key;
+                memcpy(key.data(), hs.data() + (size_t)t * 8, 32);
+                freq[key]++;
+            }
+            std::vector<std::pair<uint32_t, std::array<uint32_t, 8>>> top;
+            for (auto& kv : freq) {
+                bool zero = true;
+                for (uint32_t w : kv.first) zero = zero && w == 0;
+                if (!zero && kv.second * 100 >= taken * 3) top.push_back({kv.second, kv.first});
+            }
+            std::sort(top.begin(), top.end(), [](auto& a, auto& b) { return a.first > b.first; });
+            for (size_t j = 0; j < top.size() && j < DEDUP_MAX; j++) memcpy(dc->cd.v[dc->cd.k++], top[j].second.data(), 32);
         }
-        std::vector<std::pair<uint32_t, std::array<uint32_t, 8>>> top;
-        for (auto& kv : freq) {
-            bool zero = true;
-            for (uint32_t w : kv.first) zero = zero && w == 0;
-            if (!zero && kv.second * 100 >= taken * 3) top.push_back({kv.second, kv.first});
+        dc->scalars = scalars_dev; dc->n = n; dc->mont = mont;
+        dc->n_heavy = dc->n_rest = 0;
+        if (dc->cd.k != 0) {
+            // step 2: classify (count, then lists)
+            B2S_TRY(dc->ints.alloc(c, (3 * (DEDUP_MAX + 2)) * sizeof(uint32_t)));          // counts | offsets | cursor
+            uint32_t* counts = dc->ints.as<uint32_t>();
+            uint32_t* offs = counts + DEDUP_MAX + 2;
+            uint32_t* cursor = offs + DEDUP_MAX + 2;
+            B2S_CUDA(c, cudaMemsetAsync(dc->ints.p, 0, dc->ints.bytes, c->stream));
+            B2S_LAUNCH_N(c, "msm_classify_count", (msm_classify_kernel<Fr, 0>), cdiv(n, 256), 256, 0, scalars, n, dc->cd, counts, (const uint32_t*)offs, cursor,
+                         (uint32_t*)nullptr, (uint32_t*)nullptr, (Fr*)nullptr);
+            uint32_t hcounts[DEDUP_MAX + 1];
+            B2S_CUDA(c, cudaMemcpyAsync(hcounts, counts, sizeof(hcounts), cudaMemcpyDeviceToHost, c->stream));
+            B2S_CUDA(c, cudaStreamSynchronize(c->stream));
+            uint64_t n_heavy = 0;
+            uint32_t hoffs[DEDUP_MAX + 2] = {0};
+            for (uint32_t j = 0; j < DEDUP_MAX; j++) { hoffs[j] = (uint32_t)n_heavy; n_heavy += hcounts[j]; }
+            hoffs[DEDUP_MAX] = (uint32_t)n_heavy;
+            dc->n_heavy = n_heavy;
+            dc->n_rest = hcounts[DEDUP_MAX];
+            if (n_heavy * 8 < n) {
+                dc->cd.k = 0;       // the sample misled: not worth it
+            } else {
+                B2S_CUDA(c, cudaMemcpyAsync(offs, hoffs, sizeof(hoffs), cudaMemcpyHostToDevice, c->stream));
+                B2S_CUDA(c, cudaStreamSynchronize(c->stream));      // hoffs lives on this stack frame
+                B2S_TRY(dc->heavy_sorted.alloc(c, std::max<uint64_t>(n_heavy, 1) * sizeof(uint32_t)));
+                B2S_TRY(dc->rest_idx.alloc(c, std::max<uint64_t>(dc->n_rest, 1) * sizeof(uint32_t)));
+                B2S_TRY(dc->rest_scal.alloc(c, std::max<uint64_t>(dc->n_rest, 1) * sizeof(Fr)));
+                B2S_LAUNCH_N(c, "msm_classify_lists", (msm_classify_kernel<Fr, 1>), cdiv(n, 256), 256, 0, scalars, n, dc->cd, counts, (const uint32_t*)offs,
+                             cursor, dc->heavy_sorted.as<uint32_t>(), dc->rest_idx.as<uint32_t>(), dc->rest_scal.as<Fr>());
+            }
         }
-        std::sort(top.begin(), top.end(), [](auto& a, auto& b) { return a.first > b.first; });
-        for (size_t j = 0; j < top.size() && j < DEDUP_MAX; j++) memcpy(cd.v[cd.k++], top[j].second.data(), 32);
+        dc->valid = true;
     }
-    if (cd.k == 0) return msm_core_t<Curve, F>(c, bases, scalars, nullptr, n, mont, out, wins_ext);
-
-    // step 2: classify (count, then lists)
-    DevBuf ints, heavy_sorted, rest_idx, rest_scal, hsums;
-    B2S_TRY(ints.alloc(c, (3 * (DEDUP_MAX + 2)) * sizeof(uint32_t)));          // counts | offsets | cursor
-    uint32_t* counts = ints.as<uint32_t>();
+    if (dc->cd.k == 0) return msm_core_t<Curve, F>(c, bases, scalars, nullptr, n, mont, out, wins_ext, nullptr, pre);
+    const DedupCand cd = dc->cd;
+    const uint64_t n_heavy = dc->n_heavy, n_rest = dc->n_rest;
+    uint32_t* counts = dc->ints.as<uint32_t>();
     uint32_t* offs = counts + DEDUP_MAX + 2;
-    uint32_t* cursor = offs + DEDUP_MAX + 2;
-    B2S_CUDA(c, cudaMemsetAsync(ints.p, 0, ints.bytes, c->stream));
-    B2S_LAUNCH_N(c, "msm_classify_count", (msm_classify_kernel<Fr, 0>), cdiv(n, 256), 256, 0, scalars, n, cd, counts, (const uint32_t*)offs, cursor,
-                 (uint32_t*)nullptr, (uint32_t*)nullptr, (Fr*)nullptr);
-    uint32_t hcounts[DEDUP_MAX + 1];
-    B2S_CUDA(c, cudaMemcpyAsync(hcounts, counts, sizeof(hcounts), cudaMemcpyDeviceToHost, c->stream));
-    B2S_CUDA(c, cudaStreamSynchronize(c->stream));
-    uint64_t n_heavy = 0;
-    uint32_t hoffs[DEDUP_MAX + 2] = {0};
-    for (uint32_t j = 0; j < DEDUP_MAX; j++) { hoffs[j] = (uint32_t)n_heavy; n_heavy += hcounts[j]; }
-    hoffs[DEDUP_MAX] = (uint32_t)n_heavy;
-    const uint64_t n_rest = hcounts[DEDUP_MAX];
-    if (n_heavy * 8 < n) return msm_core_t<Curve, F>(c, bases, scalars, nullptr, n, mont, out, wins_ext);   // the sample misled: not worth it
-    B2S_CUDA(c, cudaMemcpyAsync(offs, hoffs, sizeof(hoffs), cudaMemcpyHostToDevice, c->stream));
-    B2S_TRY(heavy_sorted.alloc(c, std::max<uint64_t>(n_heavy, 1) * sizeof(uint32_t)));
-    B2S_TRY(rest_idx.alloc(c, std::max<uint64_t>(n_rest, 1) * sizeof(uint32_t)));
-    B2S_TRY(rest_scal.alloc(c, std::max<uint64_t>(n_rest, 1) * sizeof(Fr)));
-    B2S_LAUNCH_N(c, "msm_classify_lists", (msm_classify_kernel<Fr, 1>), cdiv(n, 256), 256, 0, scalars, n, cd, counts, (const uint32_t*)offs, cursor,
-                 heavy_sorted.as<uint32_t>(), rest_idx.as<uint32_t>(), rest_scal.as<Fr>());
+    DevBuf& heavy_sorted = dc->heavy_sorted;
+    DevBuf& rest_idx = dc->rest_idx;
+    DevBuf& rest_scal = dc->rest_scal;
+    DevBuf hsums;
     // step 3: heavy bucket sums (<= DEDUP_MAX buckets)
     B2S_TRY(hsums.alloc(c, DEDUP_MAX * sizeof(Pt)));
     B2S_CUDA(c, cudaMemsetAsync(hsums.p, 0, DEDUP_MAX * sizeof(Pt), c->stream));
@@ -775,7 +835,7 @@ static int32_t msm_run_t(Ctx* c, const void* bases_dev, const void* scalars_dev,
     }
     // step 4: the rest through the ordinary pipeline
     bool used_aux = false;
-    B2S_TRY((msm_core_t<Curve, F>(c, bases, rest_scal.as<Fr>(), rest_idx.as<uint32_t>(), n_rest, mont, out, wins_ext, &used_aux)));
+    B2S_TRY((msm_core_t<Curve, F>(c, bases, rest_scal.as<Fr>(), rest_idx.as<uint32_t>(), n_rest, mont, out, wins_ext, &used_aux, pre)));
     // step 5: on the stream that writes `out` (the aux stream when the Horner tail went there; the heavy sums were finished on
     // the main stream before the event the aux stream waits for)
     cudaStream_t fs = used_aux ? c->aux : c->stream;
@@ -816,11 +876,59 @@ int32_t msm_join_tails(Ctx* c) {
 }
 
 int32_t msm_run(Ctx* c, int group, const void* bases_dev, const void* scalars_dev, uint64_t n, bool scalars_mont,
-                void* out_xyzz_dev, void* wins_ext) {
+                void* out_xyzz_dev, void* wins_ext, const MsmPre* pre) {
     return dispatch_curve(c, [&](auto curve) {
         using C = decltype(curve);
-        if (group == 1) return msm_run_t<C, typename C::Fq>(c, bases_dev, scalars_dev, n, scalars_mont, out_xyzz_dev, wins_ext);
-        return msm_run_t<C, typename C::Fq2>(c, bases_dev, scalars_dev, n, scalars_mont, out_xyzz_dev, wins_ext);
+        if (group == 1) return msm_run_t<C, typename C::Fq>(c, bases_dev, scalars_dev, n, scalars_mont, out_xyzz_dev, wins_ext, pre);
+        return msm_run_t<C, typename C::Fq2>(c, bases_dev, scalars_dev, n, scalars_mont, out_xyzz_dev, wins_ext, pre);
+    });
+}
+
+// ---- fixed-base window precomputation for a resident key ----------------------------------------------------------------
+// table[w * n + i] = 2^(c w) * P_i, normalised to affine: c doublings per window step, one inversion per output (a one-off at
+// key upload).  With it the digits of ALL windows of an MSM over these bases share one set of 2^(c-1) buckets: nwin times
+// fewer buckets to reduce, no per-window sums, no Horner tail, and a shard of the key keeps the window size of the full key.
+template <class F>
+__global__ void __launch_bounds__(128) msm_precompute_kernel(const Affine<F>* __restrict__ bases, uint64_t n, uint32_t c, uint32_t nwin, Affine<F>* __restrict__ table) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const Affine<F> p = ld_struct(bases + i);
+    st_struct(table + i, p);
+    XYZZ<F> acc = XYZZ<F>::from_affine(p);
+    for (uint32_t w = 1; w < nwin; w++) {
+        for (uint32_t k = 0; k < c; k++) acc = acc.dbl();
+        const Affine<F> q = acc.to_affine();
+        st_struct(table + (uint64_t)w * n + i, q);
+        acc = XYZZ<F>::from_affine(q);          // keep the chain in the cheaper mixed form
+    }
+}
+
+uint32_t msm_precompute_windows(Ctx* c, uint64_t n, uint32_t* c_out) {
+    // one bucket set whatever the number of windows: c = 20 balances n * nwin additions against 2^(c-1) buckets from 2^18 points up
+    (void)n;
+    const uint32_t bits = c->curve == B2S_CURVE_BLS12_381 ? 255 : 254;
+    const uint32_t cc = env_u32("B2S_MSM_PRE_C", 20);
+    uint32_t nw = (bits + cc - 1) / cc;
+    if (bits - (nw - 1) * cc >= cc) nw += 1;
+    if (c_out) *c_out = cc;
+    return nw;
+}
+
+int32_t msm_precompute(Ctx* c, int group, const void* bases_dev, uint64_t n, void* table_dev, MsmPre* pre) {
+    uint32_t cc = 0;
+    const uint32_t nw = msm_precompute_windows(c, n, &cc);
+    if ((uint64_t)nw * n >= (1ull << 31)) return fail(c, B2S_ERR_INVALID_ARG, "msm_precompute: table of %u x %llu points exceeds 2^31", nw, (unsigned long long)n);
+    pre->c = cc; pre->nwin = nw; pre->stride = (uint32_t)n;
+    if (n == 0) return B2S_OK;
+    return dispatch_curve(c, [&](auto curve) {
+        using C = decltype(curve);
+        if (group == 1)
+            B2S_LAUNCH_N(c, "msm_precompute_g1", msm_precompute_kernel<typename C::Fq>, cdiv(n, 128), 128, 0, reinterpret_cast<const Affine<typename C::Fq>*>(bases_dev), n,
+                         cc, nw, reinterpret_cast<Affine<typename C::Fq>*>(table_dev));
+        else
+            B2S_LAUNCH_N(c, "msm_precompute_g2", msm_precompute_kernel<typename C::Fq2>, cdiv(n, 128), 128, 0, reinterpret_cast<const Affine<typename C::Fq2>*>(bases_dev),
+                         n, cc, nw, reinterpret_cast<Affine<typename C::Fq2>*>(table_dev));
+        return (int32_t)B2S_OK;
     });
 }
 

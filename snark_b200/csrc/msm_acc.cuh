@@ -25,6 +25,9 @@ struct MsmShape {
     uint32_t G;        // nwin * B
     uint32_t L;        // max points per task
     uint64_t max_tasks;
+    // fixed-base precomputation (resident key): the bases array also holds 2^(c w) P_i at [w * pre_stride + i], so every
+    // window's digits go to ONE bucket set (G = B) and the per-window reduction / Horner tail disappear.  0 = off.
+    uint32_t pre_stride;
 };
 
 // ---- vector loads of whole structs ---------------------------------------------------------------

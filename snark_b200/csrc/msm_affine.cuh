@@ -59,6 +59,10 @@ struct BaGeom {
     static constexpr uint32_t P2_META = 2 * PT, P2_SLOT = ba_slot_bytes(2 * PT + 16);
     // threads per CTA: the G2 slots are twice as big, so half the threads keep three CTAs per SM
     static constexpr uint32_t THREADS = THREADS_;
+    // streaming rounds: one bulk copy (TMA engine) per warp row brings the row's 64 - #singles input points, which are
+    // contiguous in the previous round's output; stage = [64 points][32 x 16 B of per-lane meta][mbarrier]
+    static constexpr uint32_t P2B_META = 64 * PT, P2B_MBAR = 64 * PT + 32 * 16, P2B_STAGE = 64 * PT + 32 * 16 + 16;
+    static constexpr uint32_t P2B_SMEM = (THREADS_ / 32) * BA_P2_STAGES * P2B_STAGE;
     static constexpr uint32_t P2_MIN_CTAS = 4;      // register cap of pass 2: 65536 / (THREADS * 4) = 128 (G1) / 256 (G2)
     static constexpr uint32_t P1_SMEM = THREADS * BA_P1_STAGES * P1_SLOT, P2_SMEM = THREADS * BA_P2_STAGES * P2_SLOT;
 };
@@ -82,6 +86,32 @@ __device__ __forceinline__ void cp_async_bytes(uint32_t smem_addr, const void* g
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// ---- bulk asynchronous copies (TMA engine, cp.async.bulk) completing on an mbarrier ----------------------------------
+__device__ __forceinline__ void mbar_init(uint32_t mbar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mbar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint32_t mbar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t smem_dst, const void* gsrc, uint32_t bytes, uint32_t mbar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_dst), "l"(gsrc), "r"(bytes), "r"(mbar)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t mbar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(mbar), "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 template <class T>
 __device__ __forceinline__ T lds_struct(uint32_t smem_addr) {
@@ -134,6 +164,29 @@ __device__ __forceinline__ uint32_t ba_next_unit(uint32_t* ctr, uint32_t lane) {
     uint32_t u = 0;
     if (lane == 0) u = atomicAdd(ctr, 1u);
     return __shfl_sync(0xffffffffu, u, 0);
+}
+
+// One output of pass 2: 1 / d from the running inverse and the stored prefix (2 multiplications), then the affine addition
+// (3 more); `inv` moves on to the previous output of the lane's chain.
+template <class F>
+__device__ __forceinline__ Affine<F> ba_output(const Affine<F>& p1, const Affine<F>& p2, bool single, F& inv, const F& pre) {
+    const uint32_t kind = ba_classify(p1, p2, single);
+    const F d = ba_denominator(kind, p1, p2);
+    const F dinv = inv * pre;
+    inv = inv * d;
+    Affine<F> res;
+    if (kind == BA_ADD || kind == BA_DBL) {
+        F num;
+        if (kind == BA_ADD) num = p2.y - p1.y;
+        else { F xx = p1.x.sqr(); num = xx.dbl() + xx; }
+        const F lam = num * dinv;
+        const F x3 = lam.sqr() - p1.x - p2.x;   // DBL: p2 == p1, so this is lambda^2 - 2 x1
+        res.x = x3;
+        res.y = lam * (p1.x - x3) - p1.y;
+    } else if (kind == BA_COPY1) res = p1;
+    else if (kind == BA_COPY2) res = p2;
+    else res = Affine<F>::inf();
+    return res;
 }
 
 // descriptor of (row q, this lane): where its inputs are
@@ -347,23 +400,7 @@ msm_ba_p2_kernel(const Affine<F>* __restrict__ bases, const uint32_t* __restrict
                     } else {
                         p2 = Affine<F>::inf();
                     }
-                    const uint32_t kind = ba_classify(p1, p2, single);
-                    const F d = ba_denominator(kind, p1, p2);
-                    const F dinv = inv * pre_cur;
-                    inv = inv * d;
-                    Affine<F> res;
-                    if (kind == BA_ADD || kind == BA_DBL) {
-                        F num;
-                        if (kind == BA_ADD) num = p2.y - p1.y;
-                        else { F xx = p1.x.sqr(); num = xx.dbl() + xx; }
-                        const F lam = num * dinv;
-                        const F x3 = lam.sqr() - p1.x - p2.x;   // DBL: p2 == p1, so this is lambda^2 - 2 x1
-                        res.x = x3;
-                        res.y = lam * (p1.x - x3) - p1.y;
-                    } else if (kind == BA_COPY1) res = p1;
-                    else if (kind == BA_COPY2) res = p2;
-                    else res = Affine<F>::inf();
-                    st_struct(out + o, res);
+                    st_struct(out + o, ba_output(p1, p2, single, inv, pre_cur));
                 }
             }
             if (t >= 0 && (uint32_t)t < nr) {
@@ -386,6 +423,88 @@ msm_ba_p2_kernel(const Affine<F>* __restrict__ bases, const uint32_t* __restrict
                     b_e2 = (b_d.flags & BA_F_SINGLE) ? 0u : sorted[b_d.in0 + 1];
                 }
             }
+            if ((uint32_t)(t + 2) < nr) {
+                a_word = bitmap[q0 + nr - 1 - (uint32_t)(t + 2)];
+                a_wr = wrank[q0 + nr - 1 - (uint32_t)(t + 2)];
+            }
+        }
+    }
+}
+
+// ---- pass 2 of the streaming rounds: operands by bulk copy --------------------------------------------------------------
+// In every round but the first the inputs of a warp row -- 64 points minus one per single output -- are CONTIGUOUS in the
+// previous round's output.  One lane arms an mbarrier with the byte count and issues ONE cp.async.bulk (TMA engine) for
+// the whole row, two rows ahead of its use; the 32 lanes wait on the barrier's phase and read their points at
+// (in0 - in0 of lane 0) * sizeof(point).  Replaces 12-24 LDGSTS per lane and row by one instruction per warp and row.
+template <class F>
+__global__ void __launch_bounds__(BaGeom<F>::THREADS, BaGeom<F>::P2_MIN_CTAS)
+msm_ba_p2_bulk_kernel(const Affine<F>* __restrict__ prev, const uint32_t* __restrict__ bitmap, const uint32_t* __restrict__ wrank,
+                      const uint32_t* __restrict__ t_out_p, uint32_t target_units, uint32_t* __restrict__ unit_ctr, const F* __restrict__ prefix,
+                      const F* __restrict__ tot_inv, Affine<F>* __restrict__ out, uint32_t dense) {
+    using Gm = BaGeom<F>;
+    constexpr uint32_t S = BA_P2_STAGES, PT = Gm::PT;
+    static_assert(S == 2, "parity bookkeeping below is written for two stages");
+    extern __shared__ uint4 ba_smem[];
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const uint32_t stage0 = (uint32_t)__cvta_generic_to_shared(ba_smem) + warp * S * Gm::P2B_STAGE;
+    if (lane == 0) {
+        mbar_init(stage0 + Gm::P2B_MBAR, 1);
+        mbar_init(stage0 + Gm::P2B_STAGE + Gm::P2B_MBAR, 1);
+        mbar_fence_init();
+    }
+    __syncwarp();
+    uint32_t uses0 = 0, uses1 = 0;     // completed phases of the two stage barriers (warp-uniform)
+    const uint32_t t_out = *t_out_p;
+    const uint32_t n_rows = (t_out + 31u) >> 5;
+    const uint32_t K = ba_rows_per_unit(n_rows, target_units);
+    const uint32_t n_units = (n_rows + K - 1) / K;
+    for (uint32_t u = ba_next_unit(unit_ctr, lane); u < n_units; u = ba_next_unit(unit_ctr, lane)) {
+        const uint32_t q0 = u * K, nr = min(K, n_rows - q0);
+        F inv = ld_struct(tot_inv + (size_t)u * 32u + lane);
+        uint32_t a_word = 0, a_wr = 0;
+        BaDesc b_d{0, 0};
+        F pre_next = F::one();
+        {
+            const uint32_t o0 = (q0 + nr - 1) * 32u + lane;
+            if (o0 < t_out) pre_next = ld_struct(prefix + o0);
+        }
+        for (int32_t t = -2; t < (int32_t)(nr + S); t++) {
+            if (t >= (int32_t)S) {
+                const uint32_t i = (uint32_t)t - S;
+                const uint32_t st = stage0 + (i & 1u) * Gm::P2B_STAGE;
+                mbar_wait(st + Gm::P2B_MBAR, (i & 1u) ? (uses1 & 1u) : (uses0 & 1u));
+                if (i & 1u) uses1++; else uses0++;
+                const uint4 meta = lds16(st + Gm::P2B_META + lane * 16u);   // point offset in the stage, -, -, flags
+                const F pre_cur = pre_next;
+                if (i + 1 < nr) {
+                    const uint32_t on = (q0 + nr - 2 - i) * 32u + lane;
+                    if (on < t_out) pre_next = ld_struct(prefix + on);
+                }
+                if (meta.w & BA_F_VALID) {
+                    const bool single = (meta.w & BA_F_SINGLE) != 0;
+                    const uint32_t o = (q0 + nr - 1 - i) * 32u + lane;
+                    const Affine<F> p1 = lds_struct<Affine<F>>(st + meta.x * PT);
+                    const Affine<F> p2 = single ? Affine<F>::inf() : lds_struct<Affine<F>>(st + (meta.x + 1u) * PT);
+                    st_struct(out + o, ba_output(p1, p2, single, inv, pre_cur));
+                }
+                __syncwarp();      // every lane is done reading this stage before it is refilled below
+            }
+            if (t >= 0 && (uint32_t)t < nr) {
+                const uint32_t st = stage0 + ((uint32_t)t & 1u) * Gm::P2B_STAGE;
+                // the row's inputs: from lane 0's first point to the last valid lane's last point
+                const uint32_t valid = __ballot_sync(0xffffffffu, (b_d.flags & BA_F_VALID) != 0);
+                const uint32_t last = 31u - (uint32_t)__clz((int)valid);          // lane 0 of a row is always valid
+                const uint32_t first_in = __shfl_sync(0xffffffffu, b_d.in0, 0);
+                const uint32_t end_in = __shfl_sync(0xffffffffu, b_d.in0 + ((b_d.flags & BA_F_SINGLE) ? 1u : 2u), (int)last);
+                sts16(st + Gm::P2B_META + lane * 16u, make_uint4(b_d.in0 - first_in, 0u, 0u, b_d.flags));
+                if (lane == 0) {
+                    const uint32_t bytes = (end_in - first_in) * PT;
+                    fence_proxy_async();                                            // generic reads of the stage before the async write
+                    mbar_expect_tx(st + Gm::P2B_MBAR, bytes);
+                    bulk_g2s(st, prev + first_in, bytes, st + Gm::P2B_MBAR);
+                }
+            }
+            if (t + 1 >= 0 && (uint32_t)(t + 1) < nr) b_d = ba_desc(a_word, a_wr, q0 + nr - 1 - (uint32_t)(t + 1), lane, t_out, dense);
             if ((uint32_t)(t + 2) < nr) {
                 a_word = bitmap[q0 + nr - 1 - (uint32_t)(t + 2)];
                 a_wr = wrank[q0 + nr - 1 - (uint32_t)(t + 2)];
@@ -534,10 +653,22 @@ static int32_t msm_ba_round_launch(Ctx* c, const char* l1, const char* li, const
         B2S_LAUNCH_N(c, l2, (msm_ba_p2_kernel<F, true>), ctas, Gm::THREADS, Gm::P2_SMEM, bases, a.sorted, prev, a.bitmap, a.wrank, a.t_out,
                      a.target_units, a.unit_ctr + 1, (const F*)prefix, (const F*)tot, out, 0u);
     } else {
-        // later rounds read the previous round's output; a staged first round reads its own pairs, two per output
-        B2S_SMEM_ATTR(c, (msm_ba_p2_kernel<F, false>), Gm::P2_SMEM);
-        B2S_LAUNCH_N(c, l2, (msm_ba_p2_kernel<F, false>), ctas, Gm::THREADS, Gm::P2_SMEM, bases, a.sorted, stage ? (const Affine<F>*)staged : prev, a.bitmap,
-                     a.wrank, a.t_out, a.target_units, a.unit_ctr + 1, (const F*)prefix, (const F*)tot, out, stage ? 1u : 0u);
+        // later rounds read the previous round's output; a staged first round reads its own pairs, two per output.  Rows are
+        // contiguous there: bulk copies (B2S_MSM_BULK=0 falls back to the per-lane cp.async ring, same results)
+        const Affine<F>* src = stage ? (const Affine<F>*)staged : prev;
+        // measured (2^24 points, profiles/r02_experiments.md): G1 pass 2 within 1 % of the cp.async ring, G2 3 % slower (a lane's
+        // two 192-byte points at a 384-byte stride conflict in shared memory) -- default: bulk for G1, ring for G2
+        const char* bulk_env = getenv("B2S_MSM_BULK");
+        const bool use_bulk = bulk_env ? bulk_env[0] != '0' : sizeof(F) <= 64;
+        if (use_bulk) {
+            B2S_SMEM_ATTR(c, msm_ba_p2_bulk_kernel<F>, Gm::P2B_SMEM);
+            B2S_LAUNCH_N(c, l2, msm_ba_p2_bulk_kernel<F>, ctas, Gm::THREADS, Gm::P2B_SMEM, src, a.bitmap, a.wrank, a.t_out, a.target_units, a.unit_ctr + 1,
+                         (const F*)prefix, (const F*)tot, out, stage ? 1u : 0u);
+        } else {
+            B2S_SMEM_ATTR(c, (msm_ba_p2_kernel<F, false>), Gm::P2_SMEM);
+            B2S_LAUNCH_N(c, l2, (msm_ba_p2_kernel<F, false>), ctas, Gm::THREADS, Gm::P2_SMEM, bases, a.sorted, src, a.bitmap, a.wrank, a.t_out,
+                         a.target_units, a.unit_ctr + 1, (const F*)prefix, (const F*)tot, out, stage ? 1u : 0u);
+        }
     }
     return B2S_OK;
 }

@@ -20,6 +20,9 @@ struct b2s_pk {
     b2s::DevBuf consts_g1;            // alpha_g1, beta_g1, delta_g1 (affine)
     b2s::DevBuf consts_g2;            // beta_g2, delta_g2 (affine)
     b2s::DevBuf a_query, b_g1_query, b_g2_query, h_query, l_query;
+    // fixed-base window table of h_query (msm_precompute): [h_pre.nwin][h_len] affine points; empty when switched off / too big
+    b2s::DevBuf h_table;
+    b2s::MsmPre h_pre{0, 0, 0};
     uint32_t a_ext = 0, b1_ext = 0, b2_ext = 0;   // 2 when this shard owns the end of the range (extra delta pairs)
     uint64_t a_off = 0, a_len = 0, b1_off = 0, b1_len = 0, b2_off = 0, b2_len = 0, h_off = 0, h_len = 0, l_off = 0, l_len = 0;
 };

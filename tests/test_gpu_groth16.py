@@ -110,6 +110,30 @@ def test_groth16_prove_matches_oracle(be):
         be.r1cs_free(m)
 
 
+def test_groth16_prove_with_h_query_table(be, monkeypatch):
+    """Fixed-base window table of the h query (csrc/msm.cu msm_precompute: 2^(c w) P_i for every window, all windows sharing
+    one bucket set) forced on for small keys: same proofs as the oracle, through the affine rounds as well."""
+    monkeypatch.setenv("B2S_PK_PRECOMP_MIN", "1")
+    monkeypatch.setenv("B2S_MSM_PRE_C", "7")          # 37 windows of 64 buckets instead of 13 of 2^19: small-key sized
+    curve = CURVES[be.curve]
+    rng = random.Random(23)
+    for rounds in (None, "2"):
+        if rounds:
+            monkeypatch.setenv("B2S_MSM_AFFINE_ROUNDS", rounds)
+        for name, mats, inst, wit in circuits(curve):
+            td = og.Trapdoor(*[rng.randrange(1, curve.r) for _ in range(5)])
+            pk = og.setup(curve, mats, len(inst), len(wit), td)
+            rr, ss = rng.randrange(curve.r), rng.randrange(curve.r)
+            A, B, C, _ = og.prove(pk, mats, inst, wit, rr, ss)
+            m, _keep = upload(be, curve, mats, len(inst), len(wit))
+            keep = []
+            pkh = be.pk_upload(make_pk_desc(curve, pk, keep))
+            a, b, c = be.groth16_prove(pkh, m, pack_fr(curve, inst), pack_fr(curve, wit), pack_fr(curve, [rr]), pack_fr(curve, [ss]))
+            assert (unpack_points(curve, 1, a)[0], unpack_points(curve, 2, b)[0], unpack_points(curve, 1, c)[0]) == (A, B, C), (name, rounds)
+            be.pk_free(pkh)
+            be.r1cs_free(m)
+
+
 def test_groth16_shards_join(be):
     """Two base-range shards + b2s_groth16_finish give the same proof as the single-GPU call."""
     from snark_b200.lib import PkDesc

@@ -29,7 +29,7 @@ def launches():
         a = agg.setdefault(k, [0, 0.0])
         a[0] += 1
         a[1] += float(r[vi].replace(",", "")) * TS[r[ui]]
-    setup = {k: v for k, v in agg.items() if k.startswith("fixed_base") or k.startswith("pow_table")}
+    setup = {k: v for k, v in agg.items() if k.startswith("fixed_base") or k.startswith("pow_table") or k.startswith("msm_precompute")}
     prove = {k: v for k, v in agg.items() if k not in setup}
     total = sum(v[1] for v in prove.values())
     out = [f"# ncu --metrics gpu__time_duration.sum --clock-control none -c 4000 python bench.py --steps 1 --warmup 1 --no-extras --no-cpu --no-verify   ({tag}, final code)",
