@@ -55,6 +55,7 @@ int32_t b2s_ctx_create(int32_t curve_id, int32_t device_ordinal, b2s_ctx** out) 
     c->curve = curve_id;
     c->device = device_ordinal;
     c->sm_count = prop.multiProcessorCount;
+    c->total_mem = (uint64_t)prop.totalGlobalMem;
     if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaStreamCreateWithFlags(&c->aux, cudaStreamNonBlocking) != cudaSuccess ||
         cudaStreamCreateWithFlags(&c->side, cudaStreamNonBlocking) != cudaSuccess ||
@@ -71,6 +72,10 @@ int32_t b2s_ctx_create(int32_t curve_id, int32_t device_ordinal, b2s_ctx** out) 
         const char* g = getenv("B2S_L2_GRAN");
         const long gran = g ? strtol(g, nullptr, 10) : 0;
         if (gran > 0) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)gran);
+    }
+    if (cudaMalloc(&c->aux_ring, b2s::Ctx::AUX_SLOT_BYTES * b2s::Ctx::AUX_SLOTS) != cudaSuccess) {
+        delete c;
+        return B2S_ERR_OOM;
     }
     // keep freed blocks in the stream-ordered pool: proofs reuse the same multi-GiB scratch every call
     cudaMemPool_t pool;
@@ -91,6 +96,7 @@ void b2s_ctx_destroy(b2s_ctx* ctx) {
     cudaStreamSynchronize(ctx->stream);
     cudaStreamSynchronize(ctx->aux);
     cudaStreamSynchronize(ctx->side);
+    if (ctx->aux_ring) cudaFree(ctx->aux_ring);
     cudaEventDestroy(ctx->ev_fork);
     cudaEventDestroy(ctx->ev_join);
     cudaStreamDestroy(ctx->side);

@@ -36,6 +36,7 @@ struct Ctx {
     std::string err;
     uint64_t launches = 0;
     int sm_count = 148;
+    uint64_t total_mem = 0;     // device memory, queried once (cudaMemGetInfo costs milliseconds with a multi-GiB pool: not per MSM)
     std::map<uint32_t, NttPlan*> ntt_plans;   // keyed by log_n
     // optional per-kernel timing (b2s_profile_*): CUDA events around every launch on `stream`
     bool profiling = false;
@@ -43,6 +44,17 @@ struct Ctx {
     std::vector<ProfRec> prof;
     void* fixed_base_tables[2] = {nullptr, nullptr};  // G1 / G2 window tables (setup.cu)
     MsmDedupCache* dedup_cache = nullptr;             // non-null between msm_dedup_scope_begin / _end (one proof)
+    // small buffers read by aux-stream kernels (heavy-list sums, tiny-rest products): a ring of persistent slots instead of
+    // stream-ordered allocations freed on the other stream -- cross-stream frees make the pool insert dependencies between
+    // the streams (observed as tens of milliseconds of main-stream stalls in some timed regions)
+    static constexpr size_t AUX_SLOT_BYTES = 16384, AUX_SLOTS = 16;
+    void* aux_ring = nullptr;
+    uint32_t aux_ring_next = 0;
+    void* aux_slot() {
+        void* p = static_cast<char*>(aux_ring) + (size_t)(aux_ring_next % AUX_SLOTS) * AUX_SLOT_BYTES;
+        aux_ring_next++;
+        return p;
+    }
 };
 
 inline int32_t fail(Ctx* c, int32_t code, const char* fmt, ...) {

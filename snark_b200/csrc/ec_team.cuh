@@ -109,4 +109,22 @@ __device__ __forceinline__ XYZZ<F> team_scalar_mul(const XYZZ<F>& p, const uint3
     return acc;
 }
 
+// k * p without a table (double-and-add, most significant bit first): for one-off products where 16 table entries of shared
+// memory per product are not worth having
+template <class F>
+__device__ __forceinline__ XYZZ<F> team_scalar_mul_plain(const XYZZ<F>& p, const uint32_t* k, int nwords) {
+    XYZZ<F> acc = XYZZ<F>::identity();
+    bool started = false;
+    for (int w = nwords - 1; w >= 0; w--) {
+        for (int b = 31; b >= 0; b--) {
+            if (started) team_dbl(acc);
+            if ((k[w] >> b) & 1u) {        // the scalar is the same in every lane of the warp
+                team_add(acc, p);
+                started = true;
+            }
+        }
+    }
+    return acc;
+}
+
 }  // namespace b2s

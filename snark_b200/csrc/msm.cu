@@ -30,6 +30,7 @@
 // bound by the fma pipe by two orders of magnitude over HBM (DESIGN.md has the numbers).
 #include <algorithm>
 #include <array>
+#include <chrono>
 #include <cstring>
 
 #include "msm_affine.cuh"
@@ -411,15 +412,19 @@ static RoundPlan plan_rounds(Ctx* c, uint64_t T, uint32_t G, bool is_g1, uint32_
         // scratch of the rounds: two output buffers, the prefix products and the lane totals (bounded by the first round)
         const uint64_t t0 = std::min<uint64_t>(T, (T + G) / 2 + 1);
         const uint64_t need = t0 * (sizeof(Affine<F>) * 3 / 2 + sizeof(F)) + t0 / 4;
-        size_t free_b = 0, total_b = 0;
-        cudaMemGetInfo(&free_b, &total_b);
+        // free-memory queries only when the scratch is a large part of the device (they cost milliseconds of host time with a
+        // multi-GiB pool, and this runs once per MSM): anything under a third of the device is simply allocated
+        size_t free_b = (size_t)c->total_mem, total_b = 0;
         uint64_t pool_held = 0;
-        cudaMemPool_t pool;
-        if (cudaDeviceGetDefaultMemPool(&pool, c->device) == cudaSuccess) {
-            uint64_t reserved = 0, used = 0;
-            cudaMemPoolGetAttribute(pool, cudaMemPoolAttrReservedMemCurrent, &reserved);
-            cudaMemPoolGetAttribute(pool, cudaMemPoolAttrUsedMemCurrent, &used);
-            pool_held = reserved > used ? reserved - used : 0;
+        if (need * 3 > c->total_mem) {
+            cudaMemGetInfo(&free_b, &total_b);
+            cudaMemPool_t pool;
+            if (cudaDeviceGetDefaultMemPool(&pool, c->device) == cudaSuccess) {
+                uint64_t reserved = 0, used = 0;
+                cudaMemPoolGetAttribute(pool, cudaMemPoolAttrReservedMemCurrent, &reserved);
+                cudaMemPoolGetAttribute(pool, cudaMemPoolAttrUsedMemCurrent, &used);
+                pool_held = reserved > used ? reserved - used : 0;
+            }
         }
         if (need + ((uint64_t)2 << 30) > (uint64_t)free_b + pool_held) rp.rounds = 0;
         // staged first round (the points of a random-access first round are fetched once and written out as pairs; 2 more
@@ -581,11 +586,20 @@ static int32_t msm_core_t(Ctx* c, const Affine<F>* bases, const typename Curve::
         B2S_CUDA(c, cudaMemsetAsync(out, 0, sizeof(Pt), c->stream));
         return B2S_OK;
     }
+    const bool host_timing = getenv("B2S_HOST_TIMING") != nullptr;
+    auto t_host0 = std::chrono::steady_clock::now();
+    auto lap = [&](const char* what) {
+        if (!host_timing) return;
+        auto t1 = std::chrono::steady_clock::now();
+        fprintf(stderr, "[b2s-host] msm_core n=%llu %-14s %.3f ms\n", (unsigned long long)n, what, std::chrono::duration<double, std::milli>(t1 - t_host0).count());
+        t_host0 = t1;
+    };
     MsmShape sh = msm_shape(n, Curve::FrP::BITS, sizeof(Pt), pre);
     if ((uint64_t)sh.nwin * n >= (1ull << 32)) return fail(c, B2S_ERR_INVALID_ARG, "msm: n * windows exceeds 2^32");
     if (pre && (uint64_t)pre->nwin * pre->stride >= (1ull << 31)) return fail(c, B2S_ERR_INVALID_ARG, "msm: precomputed table exceeds 2^31 points");
     const RoundPlan rp = plan_rounds<F>(c, (uint64_t)sh.nwin * n, sh.G, is_g1, sh.L, true);   // digits of distinct scalars: random gathers
     sh.L = rp.L; sh.max_tasks = rp.max_tasks;
+    lap("plan_rounds");
     const uint32_t MSM_SEG = env_u32("B2S_MSM_SEG", sh.B >= (1u << 16) ? 32u : 16u);
     const uint32_t ntiles = (sh.G + SCAN_TILE - 1) / SCAN_TILE;
     DevBuf ibuf, sorted, bucket_acc, segs, wins, tiles;
@@ -612,6 +626,7 @@ static int32_t msm_core_t(Ctx* c, const Affine<F>* bases, const typename Curve::
     if (!wins_ext) B2S_TRY(wins.alloc(c, (size_t)sh.nwin * sizeof(Pt)));
     Pt* wins_p = wins_ext ? reinterpret_cast<Pt*>(wins_ext) : wins.as<Pt>();
 
+    lap("allocations");
     B2S_LAUNCH(c, msm_count_kernel<Fr>, cdiv(n, 256), 256, 0, scalars, n, mont, sh, counts);
     const uint32_t* no_perm = nullptr;
     B2S_LAUNCH(c, msm_scan_tiles_kernel, ntiles, SCAN_THREADS, 0, counts, no_perm, sh, tiles.as<Scan3>());
@@ -723,6 +738,38 @@ msm_heavy_finish_kernel(const XYZZ<F>* __restrict__ sums, DedupCand cd, bool mon
     }
 }
 
+// A rest of a handful of points (the DummyCircuit witness leaves ~10) does not deserve the Pippenger pipeline -- two dozen
+// launches and a 255-doubling Horner tail for nothing: one warp per (point, scalar) product, then one warp sums.
+static constexpr uint32_t TINY_REST = 24;
+template <class Curve, class F>
+__global__ void __launch_bounds__(32)
+msm_tiny_products_kernel(const Affine<F>* __restrict__ bases, const uint32_t* __restrict__ rest_idx, const typename Curve::Fr* __restrict__ rest_scal, uint32_t n_rest,
+                         const XYZZ<F>* __restrict__ heavy_sums, DedupCand cd, bool mont, XYZZ<F>* __restrict__ prods) {
+    using Fr = typename Curve::Fr;
+    const uint32_t j = blockIdx.x;      // j < n_rest: rest element j;  else heavy list j - n_rest
+    Fr v;
+    XYZZ<F> p;
+    if (j < n_rest) {
+        v = ld_struct(rest_scal + j);
+        p = XYZZ<F>::from_affine(ld_struct(bases + rest_idx[j]));
+    } else {
+#pragma unroll
+        for (int t = 0; t < 8; t++) v.v[t] = cd.v[j - n_rest][t];
+        p = ld_struct(heavy_sums + (j - n_rest));
+    }
+    if (mont) v = v.from_mont();
+    else { v = v.to_mont(); v = v.from_mont(); }
+    __shared__ XYZZ<F> table[16];
+    const XYZZ<F> r = team_scalar_mul(p, v.v, Fr::N, table);
+    if (threadIdx.x == 0) st_struct(prods + j, r);
+}
+template <class F>
+__global__ void __launch_bounds__(32) msm_tiny_sum_kernel(const XYZZ<F>* __restrict__ prods, uint32_t count, XYZZ<F>* __restrict__ out) {
+    XYZZ<F> acc = XYZZ<F>::identity();
+    for (uint32_t j = 0; j < count; j++) team_add(acc, ld_struct(prods + j));
+    if (threadIdx.x == 0) st_struct(out, acc);
+}
+
 }  // namespace b2s
 struct b2s::MsmDedupCache {
     bool valid = false;
@@ -756,6 +803,11 @@ static int32_t msm_run_t(Ctx* c, const void* bases_dev, const void* scalars_dev,
     MsmDedupCache* dc = c->dedup_cache ? c->dedup_cache : &local;
     const bool hit = dc->valid && dc->scalars == scalars_dev && dc->n == n && dc->mont == mont;
     if (!hit) {
+        if (dc->valid && c->aux_pending) {
+            // the lists about to be replaced may still be read by tiny-rest kernels of earlier MSMs on the aux stream
+            B2S_CUDA(c, cudaEventRecord(c->ev_done, c->aux));
+            B2S_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_done, 0));
+        }
         dc->valid = false;
         dc->cd = DedupCand{};
         if (n >= env_u32("B2S_MSM_DEDUP_MIN", 1u << 16) && env_u32("B2S_MSM_DEDUP", 1)) {
@@ -825,13 +877,32 @@ static int32_t msm_run_t(Ctx* c, const void* bases_dev, const void* scalars_dev,
     DevBuf& heavy_sorted = dc->heavy_sorted;
     DevBuf& rest_idx = dc->rest_idx;
     DevBuf& rest_scal = dc->rest_scal;
-    DevBuf hsums;
+    // heavy-list sums and (tiny rest) products: read by aux-stream kernels, so they live in the ctx's persistent slot ring
+    static_assert((DEDUP_MAX + TINY_REST + DEDUP_MAX) * sizeof(XYZZ<F>) <= Ctx::AUX_SLOT_BYTES, "aux slot too small");
+    Pt* const hsums = reinterpret_cast<Pt*>(c->aux_slot());
+    Pt* const prods_ring = hsums + DEDUP_MAX;
     // step 3: heavy bucket sums (<= DEDUP_MAX buckets)
-    B2S_TRY(hsums.alloc(c, DEDUP_MAX * sizeof(Pt)));
-    B2S_CUDA(c, cudaMemsetAsync(hsums.p, 0, DEDUP_MAX * sizeof(Pt), c->stream));
+    B2S_CUDA(c, cudaMemsetAsync(hsums, 0, DEDUP_MAX * sizeof(Pt), c->stream));
     {
         const RoundPlan rp = plan_rounds<F>(c, n_heavy, DEDUP_MAX, is_g1, (uint32_t)std::max<uint64_t>(64, n_heavy >> 18), false);   // lists in index order: the gathers stream
-        B2S_TRY((bucket_sums_t<Curve, F>(c, bases, heavy_sorted.as<uint32_t>(), counts, offs, n_heavy, DEDUP_MAX, rp, hsums.as<Pt>())));
+        B2S_TRY((bucket_sums_t<Curve, F>(c, bases, heavy_sorted.as<uint32_t>(), counts, offs, n_heavy, DEDUP_MAX, rp, hsums)));
+    }
+    if (n_rest <= TINY_REST && !getenv("B2S_MSM_NO_TINY")) {
+        // steps 4 + 5 for a tiny rest: every product v * P (rest) and v_j * S_j (heavy) in its own warp, then one sum
+        const uint32_t count = (uint32_t)n_rest + cd.k;
+        Pt* const prods = prods_ring;
+        // latency-bound (255 dependent doublings): inside a proof it goes to the aux stream, under the next MSM
+        const bool on_aux = wins_ext != nullptr && !getenv("B2S_NO_AUX");
+        cudaStream_t ts = on_aux ? c->aux : c->stream;
+        if (on_aux) {
+            B2S_CUDA(c, cudaEventRecord(c->ev_tail, c->stream));
+            B2S_CUDA(c, cudaStreamWaitEvent(c->aux, c->ev_tail, 0));
+        }
+        B2S_LAUNCH_SN(c, ts, is_g1 ? "msm_tiny_products_g1" : "msm_tiny_products_g2", (msm_tiny_products_kernel<Curve, F>), count, 32, 0, bases,
+                      (const uint32_t*)rest_idx.as<uint32_t>(), (const Fr*)rest_scal.as<Fr>(), (uint32_t)n_rest, (const Pt*)hsums, cd, mont, prods);
+        B2S_LAUNCH_SN(c, ts, is_g1 ? "msm_tiny_sum_g1" : "msm_tiny_sum_g2", msm_tiny_sum_kernel<F>, 1, 32, 0, (const Pt*)prods, count, out);
+        if (on_aux) c->aux_pending = true;
+        return B2S_OK;
     }
     // step 4: the rest through the ordinary pipeline
     bool used_aux = false;
@@ -842,11 +913,7 @@ static int32_t msm_run_t(Ctx* c, const void* bases_dev, const void* scalars_dev,
     const size_t fin_smem = ((size_t)DEDUP_MAX * 16 + DEDUP_MAX) * sizeof(Pt);
     B2S_SMEM_ATTR(c, (msm_heavy_finish_kernel<Curve, F>), fin_smem);
     B2S_LAUNCH_SN(c, fs, is_g1 ? "msm_heavy_finish_g1" : "msm_heavy_finish_g2", (msm_heavy_finish_kernel<Curve, F>), 1, 32 * DEDUP_MAX, fin_smem,
-                  (const Pt*)hsums.as<Pt>(), cd, mont, out);
-    if (used_aux) {
-        cudaFreeAsync(hsums.p, c->aux);   // the buffer must outlive the aux-stream kernel: freed in that stream's order
-        hsums.p = nullptr;
-    }
+                  (const Pt*)hsums, cd, mont, out);
     return B2S_OK;
 }
 
