@@ -130,11 +130,19 @@ dspmv_kernel(DSpmvMat m0, DSpmvMat m1, DSpmvMat m2, const Fr* __restrict__ pool,
     gst<Fr>(reinterpret_cast<Fr*>(m.out) + loc, acc);
 }
 
+// a *= b on the coset; later, on coefficients, h = (q - c) * zinv: the c term of (a b - c) / Z never needs its own coset
+// transform, because Z is constant on the coset and deg C < N (r1cs.cu, witness_map_t)
 template <class Fr>
-__global__ void __launch_bounds__(256) dqap_pointwise_kernel(Fr* a, const Fr* b, const Fr* c, const Fr* zinv, uint64_t n) {
+__global__ void __launch_bounds__(256) dqap_mul_kernel(Fr* a, const Fr* b, uint64_t n) {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    gst<Fr>(a + i, (gld<Fr>(a + i) * gld<Fr>(b + i) - gld<Fr>(c + i)) * gld<Fr>(zinv));
+    gst<Fr>(a + i, gld<Fr>(a + i) * gld<Fr>(b + i));
+}
+template <class Fr>
+__global__ void __launch_bounds__(256) dqap_quotient_kernel(Fr* q, const Fr* c, const Fr* zinv, uint64_t n) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    gst<Fr>(q + i, (gld<Fr>(q + i) - gld<Fr>(c + i)) * gld<Fr>(zinv));
 }
 template <class Fr, class FrP>
 __global__ void dvanishing_inv_kernel(Fr* out, uint64_t domain) {
@@ -308,11 +316,13 @@ static int32_t witness_map_dist_t(Ctx* c, const b2s_r1cs* m, const void* z_dev, 
             for (int v = 0; v < nv; v++) B2S_TRY((dntt_half2<Curve>(c, q, ranks[r], recv(r, v), data(r, v), inverse, coset)));
         return B2S_OK;
     };
-    B2S_TRY(transform(3, true, false));
-    B2S_TRY(transform(3, false, true));
+    B2S_TRY(transform(3, true, false));      // a, b, c -> coefficients (every transform maps the local layout onto itself)
+    B2S_TRY(transform(2, false, true));      // a, b -> coset evaluations; c stays in coefficient form
     for (size_t r = 0; r < R; r++)
-        B2S_LAUNCH_N(c, "dqap_pointwise_kernel", dqap_pointwise_kernel<Fr>, cdiv(local, 256), 256, 0, data(r, 0), data(r, 1), data(r, 2), zi.as<Fr>(), local);
+        B2S_LAUNCH_N(c, "dqap_mul_kernel", dqap_mul_kernel<Fr>, cdiv(local, 256), 256, 0, data(r, 0), (const Fr*)data(r, 1), local);
     B2S_TRY(transform(1, true, true));
+    for (size_t r = 0; r < R; r++)
+        B2S_LAUNCH_N(c, "dqap_quotient_kernel", dqap_quotient_kernel<Fr>, cdiv(local, 256), 256, 0, data(r, 0), (const Fr*)data(r, 2), (const Fr*)zi.as<Fr>(), local);
     // h into contiguous coefficient slabs: rows i1 in [d N1/G, (d+1) N1/G) of the local layout are one contiguous block
     {
         std::vector<const void*> s(R);

@@ -15,6 +15,20 @@ struct PowTab {
     uint32_t a = 0;
 };
 
+// Full-size factor tables of a plan (ntt.cu, built on the first single-GPU transform of that size).  The passes are bound by the
+// integer-multiply pipe while DRAM sits at ~7 %: reading a precomputed factor (32 B per element, streamed like the data) is
+// free, composing it from two small tables costs a multiplication per element.
+struct NttFull {
+    DevBuf buf;
+    const void* bnd[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};   // [inverse][pass]: inter-pass twiddles, entry k * 2^log_m + m
+    const void* wr[2][3] = {{nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr}};   // [inverse][pass]: butterfly twiddles w_R^e, e < R/2
+    // witness-map scalings (r1cs.cu): input g^j / N for the coset NTT behind an UNSCALED inverse transform, output
+    // g^-j * Zinv / N for the closing coset inverse transform
+    const void* wm_pre = nullptr;
+    const void* wm_post = nullptr;
+    const void* wm_beta = nullptr;   // one element: Zinv / N
+};
+
 struct NttPlan {
     uint32_t log_n = 0;
     int npass = 0;
@@ -22,6 +36,11 @@ struct NttPlan {
     DevBuf tables;     // all pow tables, contiguous
     PowTab fwd, inv, coset_in, coset_out_scaled;
     const void* n_inv = nullptr;   // one element: N^-1 (plain iNTT output scaling)
+    const void* zinv = nullptr;    // one element: (g^N - 1)^-1, the vanishing polynomial's inverse on the coset g H
+    const void* one = nullptr;     // one element: 1
+    bool full_tried = false;
+    NttFull* full = nullptr;       // nullptr: factors are composed from the two-level tables
+    ~NttPlan() { delete full; }
 };
 
 template <class Fr>
@@ -103,6 +122,15 @@ __device__ __forceinline__ uint32_t bitrev(uint32_t x, uint32_t bits) { return b
 
 // plan (tables) for 2^log_n on this ctx, built on first use (ntt.cu)
 int32_t ntt_get_plan(Ctx* c, uint32_t log_n, NttPlan** out);
+// Transform modes.  INVERSE / COSET are ark-poly's four transforms (ifft scales by 1/N, the coset forms scale by g^j on the
+// way in / g^-j on the way out).  WM marks the three variants witness_map chains together (they need plan->full):
+//   WM | INVERSE           inverse transform WITHOUT the 1/N scaling
+//   WM | COSET             forward coset transform whose input scaling is g^j / N   (makes up for the line above)
+//   WM | INVERSE | COSET   inverse coset transform whose output scaling is g^-j * Zinv / N
+enum : uint32_t { NTT_M_INVERSE = 1, NTT_M_COSET = 2, NTT_M_WM = 4 };
+int32_t ntt_run_mode(Ctx* c, void* data_dev, uint32_t log_n, uint32_t mode);
+// plan with full-size tables, or *out = nullptr when they are switched off (B2S_NTT_FULL=0) or would not fit
+int32_t ntt_get_full(Ctx* c, uint32_t log_n, NttPlan** out);
 // dynamic shared memory of one pass CTA (tile of 1024 elements at pitch 2C+1, butterfly twiddles behind it)
 inline size_t ntt_pass_smem_bytes() {
     return ((size_t)(1u << NTT_TILE_LOG) * 2 + (1u << NTT_MAX_RADIX_LOG) + 2) * sizeof(uint4) + (size_t)(1u << (NTT_MAX_RADIX_LOG - 1)) * 32;

@@ -16,6 +16,7 @@
 #define B2S_INLINE_MUL 1   // Fr only in this unit
 #include <unordered_map>
 
+#include "ntt.cuh"
 #include "r1cs.cuh"
 
 namespace b2s {
@@ -70,23 +71,19 @@ __global__ void copy_instance_kernel(Fr* a, const Fr* z, uint64_t n_rows, uint64
     if (i < n_instance) fr_st(a + n_rows + i, fr_ld(z + i));
 }
 
-// zinv = (g^N - 1)^-1
-template <class Fr, class FrP>
-__global__ void vanishing_inv_kernel(Fr* out, uint64_t domain) {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    Fr g;
-    for (int i = 0; i < Fr::N; i++) g.v[i] = FrP::gen(i);
-    Fr t = g.pow_u64(domain) - Fr::one();
-    out[0] = t.inverse();
-}
-
-// K3: ab[i] = (a[i] b[i] - c[i]) * zinv   (in place over a)
+// K3, first half: a[i] *= b[i]   (evaluations of A B on the coset g H)
 template <class Fr>
-__global__ void __launch_bounds__(256) qap_pointwise_kernel(Fr* a, const Fr* b, const Fr* c, const Fr* zinv, uint64_t n) {
+__global__ void __launch_bounds__(256) qap_mul_kernel(Fr* a, const Fr* b, uint64_t n) {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    Fr x = fr_ld(a + i), y = fr_ld(b + i), w = fr_ld(c + i);
-    fr_st(a + i, (x * y - w) * fr_ld(zinv));
+    fr_st(a + i, fr_ld(a + i) * fr_ld(b + i));
+}
+// K3, second half, on COEFFICIENTS: h[j] = q[j] * alpha - c[j] * beta   (in place over q; alpha, beta one element each)
+template <class Fr>
+__global__ void __launch_bounds__(256) qap_quotient_kernel(Fr* q, const Fr* c, const Fr* alpha, const Fr* beta, uint64_t n) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    fr_st(q + i, fr_ld(q + i) * fr_ld(alpha) - fr_ld(c + i) * fr_ld(beta));
 }
 
 // -------------------------------------------------------------------------------------------
@@ -200,16 +197,20 @@ int32_t spmv_run(Ctx* c, const b2s_r1cs* m, const void* z_dev, void* oa, void* o
     return dispatch_curve(c, [&](auto curve) { return spmv_t<decltype(curve)>(c, m, z_dev, oa, ob, oc); });
 }
 
+// h = coefficients of (A B - C) / Z.  ark-groth16 evaluates a, b AND c on the coset g H, forms
+// (a b - c) / Z there and interpolates: 7 transforms.  Z is the constant g^N - 1 on that coset and C has degree < N, so the
+// interpolation of the c term gives back C's own coefficients: h = (cosetiNTT(a_coset * b_coset) - iNTT(c)) * Zinv, exactly,
+// for every assignment (satisfying or not) -- 6 transforms, the same field elements.  With the plan's full-size tables the
+// scalings are merged as well: the three inverse transforms run unscaled, the 1/N goes into the coset input scaling of a and
+// b (g^j / N), Zinv into the output scaling of the closing transform, and c's 1/N * Zinv into the (HBM-bound) last kernel.
 template <class Curve>
 static int32_t witness_map_t(Ctx* c, const b2s_r1cs* m, const void* z_dev, void* h_dev) {
     using Fr = typename Curve::Fr;
-    using FrP = typename Curve::FrP;
     const uint64_t N = 1ull << m->log_domain;
     Fr* a = reinterpret_cast<Fr*>(h_dev);
-    DevBuf bb, cb, zi;
+    DevBuf bb, cb;
     B2S_TRY(bb.alloc(c, N * sizeof(Fr)));
     B2S_TRY(cb.alloc(c, N * sizeof(Fr)));
-    B2S_TRY(zi.alloc(c, sizeof(Fr)));
     Fr* b = bb.as<Fr>();
     Fr* cc = cb.as<Fr>();
     // zero the padding [n_rows, N)
@@ -219,12 +220,20 @@ static int32_t witness_map_t(Ctx* c, const b2s_r1cs* m, const void* z_dev, void*
     B2S_TRY(spmv_t<Curve>(c, m, z_dev, a, b, cc));
     B2S_LAUNCH(c, copy_instance_kernel<Fr>, cdiv(m->n_instance, 256), 256, 0, a, reinterpret_cast<const Fr*>(z_dev),
                m->n_rows, m->n_instance);
-    B2S_LAUNCH(c, (vanishing_inv_kernel<Fr, FrP>), 1, 32, 0, zi.as<Fr>(), N);
+    NttPlan* pl = nullptr;
+    B2S_TRY(ntt_get_full(c, m->log_domain, &pl));
+    const uint32_t wm = pl ? NTT_M_WM : 0u;
+    if (!pl) B2S_TRY(ntt_get_plan(c, m->log_domain, &pl));
     Fr* bufs[3] = {a, b, cc};
-    for (Fr* v : bufs) B2S_TRY(ntt_run(c, v, m->log_domain, true, false));
-    for (Fr* v : bufs) B2S_TRY(ntt_run(c, v, m->log_domain, false, true));
-    B2S_LAUNCH(c, qap_pointwise_kernel<Fr>, cdiv(N, 256), 256, 0, a, b, cc, zi.as<Fr>(), N);
-    B2S_TRY(ntt_run(c, a, m->log_domain, true, true));
+    for (Fr* v : bufs) B2S_TRY(ntt_run_mode(c, v, m->log_domain, NTT_M_INVERSE | wm));
+    B2S_TRY(ntt_run_mode(c, a, m->log_domain, NTT_M_COSET | wm));
+    B2S_TRY(ntt_run_mode(c, b, m->log_domain, NTT_M_COSET | wm));
+    B2S_LAUNCH(c, qap_mul_kernel<Fr>, cdiv(N, 256), 256, 0, a, (const Fr*)b, N);
+    B2S_TRY(ntt_run_mode(c, a, m->log_domain, NTT_M_INVERSE | NTT_M_COSET | wm));
+    // composed scalings: q and c both still lack Zinv;  merged: q is finished, c lacks Zinv / N
+    const Fr* alpha = reinterpret_cast<const Fr*>(wm ? pl->one : pl->zinv);
+    const Fr* beta = reinterpret_cast<const Fr*>(wm ? pl->full->wm_beta : pl->zinv);
+    B2S_LAUNCH(c, qap_quotient_kernel<Fr>, cdiv(N, 256), 256, 0, a, (const Fr*)cc, alpha, beta, N);
     return B2S_OK;
 }
 

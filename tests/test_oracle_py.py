@@ -232,3 +232,44 @@ def test_compressed_encoding_known_vectors():
     assert oser.point_compressed(BN254, 1, g.gen) == (1).to_bytes(32, "little")
     assert oser.point_compressed(BN254, 1, g.neg(g.gen))[-1] & 0x80
     assert len(oser.proof_compressed(BN254, g.gen, groups(BN254)[1].gen, None)) == 128
+
+
+@pytest.mark.parametrize("curve", [BLS12_381, BN254], ids=["bls12_381", "bn254"])
+def test_witness_map_six_transform_identity(curve):
+    """The product computes h with 6 transforms instead of ark-groth16's 7 (snark_b200/csrc/r1cs.cu, witness_map_t):
+    Z is the constant g^N - 1 on the coset and deg C < N, so the c term needs no coset round trip.  Pin the identity, in
+    the composed form and in the merged-scaling form the kernels use, against the oracle's 7-transform witness_map -- for a
+    satisfying AND a non-satisfying assignment (the identity does not depend on a*b = c holding on the domain)."""
+    r, g = curve.r, curve.fr_generator
+    for cs in (orc.circuit2(curve, 1, 1, 2), orc.dummy_circuit(curve, 3, 5, 8, 8), orc.bench_circuit(curve, 11, seed=3)):
+        cs.finalize()
+        mats, inst, wit = cs.to_matrices(), cs.instance_assignment, cs.witness_assignment
+        for bump in (0, 1):
+            z = list(inst) + list(wit)
+            z[-1] = (z[-1] + bump) % r
+            want = og.witness_map(curve, mats, z, len(inst))
+            A, B, C = mats
+            n, N = len(A), og.domain_size(len(A), len(inst))
+            a = orc.mat_vec_mul(r, A, z) + [0] * (N - n)
+            b = orc.mat_vec_mul(r, B, z) + [0] * (N - n)
+            c = orc.mat_vec_mul(r, C, z) + [0] * (N - n)
+            for i in range(len(inst)):
+                a[n + i] = z[i]
+            zinv = pow((pow(g, N, r) - 1) % r, -1, r)
+            n_inv = pow(N, -1, r)
+            # composed: standard transforms, h = (cosetiNTT(a_coset * b_coset) - iNTT(c)) * Zinv
+            ac, bc, cc = (ontt.ntt(curve, v, inverse=True) for v in (a, b, c))
+            ae, be = ontt.coset_ntt(curve, ac), ontt.coset_ntt(curve, bc)
+            q = ontt.coset_intt(curve, [x * y % r for x, y in zip(ae, be)])
+            assert [(x - y) * zinv % r for x, y in zip(q, cc)] == want
+            # merged: unscaled inverse transforms (N * coefficients), input scaling g^j / N, output scaling g^-j Zinv / N,
+            # c's 1/N and Zinv folded into the last subtraction
+            raw = [[x * N % r for x in v] for v in (ac, bc, cc)]
+            ae2 = ontt.ntt(curve, [x * pow(g, j, r) * n_inv % r for j, x in enumerate(raw[0])])
+            be2 = ontt.ntt(curve, [x * pow(g, j, r) * n_inv % r for j, x in enumerate(raw[1])])
+            assert ae2 == ae and be2 == be
+            q_raw = [x * N % r for x in ontt.ntt(curve, [x * y % r for x, y in zip(ae2, be2)], inverse=True)]
+            g_inv = pow(g, -1, r)
+            qz = [x * pow(g_inv, j, r) * n_inv * zinv % r for j, x in enumerate(q_raw)]
+            beta = zinv * n_inv % r
+            assert [(x - y * beta) % r for x, y in zip(qz, raw[2])] == want
