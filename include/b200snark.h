@@ -254,6 +254,23 @@ int32_t b2s_pk_serialize(b2s_ctx* ctx, const b2s_pk* pk, const uint8_t* vk_bytes
 int32_t b2s_fixed_base_g1(b2s_ctx* ctx, const void* scalars, uint64_t n, int32_t scalars_mont, int32_t mem, void* out);
 int32_t b2s_fixed_base_g2(b2s_ctx* ctx, const void* scalars, uint64_t n, int32_t scalars_mont, int32_t mem, void* out);
 
+/* ---- element-wise polynomial kernels: universal-setup (Marlin-style) path, SURVEY 8(f) row 4 -----
+ * The reference declares that path as a trait only (UniversalSetupSNARK, snark/src/lib.rs:107-133: universal_setup / index,
+ * then SNARK::prove, lib.rs:50-54); ark-marlin's AHP is generic over ark-poly-commit's `PolynomialCommitment` and ark-poly's
+ * `EvaluationDomain`.  A binding accelerates those two seams: commit / open = b2s_msm_g1 over the SRS (itself
+ * b2s_fixed_base_g1 of the powers of tau), every fft / ifft / coset form = b2s_ntt, matrix products = b2s_spmv, and the
+ * element-wise arithmetic in between (ark-poly `Evaluations` / `DensePolynomial` operators, ark-ff `batch_inversion`) = the
+ * three entry points below.  Vectors: Fr in Montgomery form, `n` elements, all in `mem`; scalars (s, c, z): ONE Montgomery Fr
+ * on the HOST.  Device-memory calls are queued on the ctx stream and return without synchronising (b2s_poly_eval
+ * synchronises: it returns a value).
+ *   b2s_poly_op   op 0: out = a * b   1: a + b   2: a - b   3: a * s   4: a + s   5: 1 / a with 0 -> 0 (batched inversion;
+ *                 not in place).  b is ignored for ops 3-5, s for ops 0-2 and 5.  out may alias a or b for ops 0-4.
+ *   b2s_poly_geom out[i] = c * s^i                      (domain elements, coset points, shifted powers)
+ *   b2s_poly_eval *out = sum_i coeffs[i] z^i            (out: one Montgomery Fr on the HOST) */
+int32_t b2s_poly_op(b2s_ctx* ctx, int32_t op, const void* a, const void* b, const void* s, void* out, uint64_t n, int32_t mem);
+int32_t b2s_poly_geom(b2s_ctx* ctx, const void* c, const void* s, uint64_t n, int32_t mem, void* out);
+int32_t b2s_poly_eval(b2s_ctx* ctx, const void* coeffs, uint64_t n, const void* z, int32_t mem, void* out);
+
 /* ---- element-wise field kernels (unit tests of the device arithmetic; K3 building blocks) -------
  * op: 0 mul, 1 add, 2 sub, 3 inverse(a), 4 neg(a), 5 to_mont(a), 6 from_mont(a), 7 sqr(a).
  * field: 0 = Fq, 1 = Fr of the ctx's curve.  HOST buffers of `count` elements. */

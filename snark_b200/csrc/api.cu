@@ -15,6 +15,10 @@ struct b2s_ctx : public b2s::Ctx {};
 namespace b2s {
 int32_t field_op_run(Ctx* c, int field, int op, const void* a, const void* b, void* out, uint64_t count);
 int32_t group_op_run(Ctx* c, int group, int op, const void* a, const void* b, const void* k, void* out, uint64_t count);
+// poly.cu
+int32_t poly_op_run(Ctx* c, int op, const void* a, const void* b, const void* s_host, void* out, uint64_t n, int32_t mem);
+int32_t poly_geom_run(Ctx* c, const void* c_host, const void* s_host, uint64_t n, int32_t mem, void* out);
+int32_t poly_eval_run(Ctx* c, const void* coeffs, uint64_t n, const void* z_host, int32_t mem, void* out_host);
 int32_t fixed_base_run(Ctx* c, int group, const void* scalars_dev, uint64_t n, bool mont, void* out_dev);
 void fixed_base_free(Ctx* c);
 int32_t serialize_points(Ctx* c, int group, const void* affine_host, uint32_t count, uint8_t* out, uint64_t cap);
@@ -207,6 +211,20 @@ int32_t b2s_g1_sum(b2s_ctx* ctx, const void* xyzz, uint32_t count, void* out_aff
 int32_t b2s_g2_sum(b2s_ctx* ctx, const void* xyzz, uint32_t count, void* out_affine) {
     LOCK(ctx);
     return sum_common(ctx, 2, xyzz, count, out_affine);
+}
+
+// ---- element-wise polynomial kernels (universal-setup path) ----------------------------------------
+int32_t b2s_poly_op(b2s_ctx* ctx, int32_t op, const void* a, const void* b, const void* s, void* out, uint64_t n, int32_t mem) {
+    LOCK(ctx);
+    return poly_op_run(ctx, op, a, b, s, out, n, mem);
+}
+int32_t b2s_poly_geom(b2s_ctx* ctx, const void* c, const void* s, uint64_t n, int32_t mem, void* out) {
+    LOCK(ctx);
+    return poly_geom_run(ctx, c, s, n, mem, out);
+}
+int32_t b2s_poly_eval(b2s_ctx* ctx, const void* coeffs, uint64_t n, const void* z, int32_t mem, void* out) {
+    LOCK(ctx);
+    return poly_eval_run(ctx, coeffs, n, z, mem, out);
 }
 
 // ---- element-wise test kernels ------------------------------------------------------------------

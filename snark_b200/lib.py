@@ -90,6 +90,9 @@ SIGNATURES = {
     "b2s_group_destroy": (None, [c_void_p]),
     "b2s_groth16_prove_group": (c_int32, [c_void_p] * 10),
     "b2s_groth16_prove_group_resident": (c_int32, [c_void_p] * 9),
+    "b2s_poly_op": (c_int32, [c_void_p, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_uint64, c_int32]),
+    "b2s_poly_geom": (c_int32, [c_void_p, c_void_p, c_void_p, c_uint64, c_int32, c_void_p]),
+    "b2s_poly_eval": (c_int32, [c_void_p, c_void_p, c_uint64, c_void_p, c_int32, c_void_p]),
     "b2s_field_op": (c_int32, [c_void_p, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_uint64]),
     "b2s_group_op": (c_int32, [c_void_p, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_uint64]),
 }

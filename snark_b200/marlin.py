@@ -210,21 +210,31 @@ def divide_by_vanishing(be, coeffs, size: int):
     return be.concat([s1, s2, s3]), rem
 
 
+def assign(be, pk: ProverKey, x: List[int], w: List[int]):
+    """The full assignment z = instance || witness (constraint_system.rs:193-206) laid out over H: variable j at position
+    pk.pos[j], unused positions zero.  Returns the backend vector `prove_assigned` consumes (the per-proof upload)."""
+    info = pk.info
+    assert len(x) == info.n_inst and len(x) + len(w) == info.n_vars
+    z_h = [0] * info.n
+    for j, v in enumerate(list(x) + list(w)):
+        z_h[pk.pos[j]] = v % be.r
+    return be.from_ints(z_h)
+
+
 def prove(be, pk: ProverKey, x: List[int], w: List[int], check: bool = False) -> Proof:
     """`SNARK::prove` (snark/src/lib.rs:50-54) for the universal-setup scheme.  x: instance assignment (x[0] = 1),
     w: witness assignment (constraint_system.rs:193-206)."""
+    return prove_assigned(be, pk, x, assign(be, pk, x, w), check)
+
+
+def prove_assigned(be, pk: ProverKey, x: List[int], z_h, check: bool = False) -> Proof:
     r, info, srs = be.r, pk.info, pk.srs
     n, m, l = info.n, info.m, info.l
     g = be.coset_gen
-    assert len(x) == info.n_inst and len(x) + len(w) == info.n_vars
     tr = start_transcript(r, be.fq_bytes, info, pk.index_comms, x)
     dbg = {}
 
     # ---- round 1: w^, z_A^, z_B^ -----------------------------------------------------------------------------------------
-    z_h = [0] * n
-    for j, v in enumerate(list(x) + list(w)):
-        z_h[pk.pos[j]] = v % r
-    z_h = be.from_ints(z_h)
     zA_e, zB_e, _ = be.spmv(pk.mat_handle, z_h, n)                    # evaluations over H (rows >= n_rows are zero)
     x_coeffs = be.ntt(be.from_ints([v % r for v in x] + [0] * (l - len(x))), inverse=True)      # x^ over H_X, degree < l
     x_h = be.ntt(be.pad(x_coeffs, n))                                 # x^ on H
