@@ -67,7 +67,7 @@ def traffic():
     return tr + tw
 
 
-def full(name, outname):
+def full(name, outname, header=None):
     rows = list(csv.reader(open(G + name)))
     hdr, units = rows[0], rows[1]
     want = ["gpu__time_duration.sum", "sm__pipe_fmaheavy_cycles_active.avg.pct_of_peak_sustained_elapsed", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
@@ -77,7 +77,7 @@ def full(name, outname):
             "smsp__issue_active.avg.pct_of_peak_sustained_active", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum",
             "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active",
             "launch__shared_mem_per_block_dynamic", "smsp__thread_inst_executed_per_inst_executed.ratio"]
-    out = [f"# ncu --set full --import-source on --clock-control none -k regex:msm_ba_p -c 2 python tools/msm_probe.py 24 1   ({tag}, final code; uniform scalars, FIRST round)",
+    out = [header or f"# ncu --set full --import-source on --clock-control none -k regex:msm_ba_p -c 2 python tools/msm_probe.py 24 1   ({tag}, final code; uniform scalars, FIRST round)",
            "# raw page of the report, the metrics the design argues with; stall reasons as shares of the sampled warp states"]
     for r in rows[2:]:
         out.append("\n## " + r[hdr.index("Kernel Name")][:110])
@@ -93,7 +93,9 @@ def full(name, outname):
 
 
 if __name__ == "__main__":
-    for fn, args in ((launches, ()), (traffic, ()), (full, (f"{tag}_final_ba_g1_raw.csv", f"{tag}_msm_ba_p1_p2_g1_ncu.txt"))):
+    ntt_hdr = "# ncu --set full --clock-control none -k regex:ntt_pass --launch-skip 3 -c 3 python tools/ntt_probe.py 24   (the three passes of one 2^24 forward NTT, twiddles streamed from the plan's full-size tables)"
+    for fn, args in ((launches, ()), (traffic, ()), (full, (f"{tag}_final_ba_g1_raw.csv", f"{tag}_msm_ba_p1_p2_g1_ncu.txt")),
+                     (full, (f"{tag}_ntt_full_raw.csv", f"{tag}_ntt_full_ncu.txt", ntt_hdr))):
         try:
             print(fn.__name__, fn(*args))
         except FileNotFoundError as e:
