@@ -7,6 +7,7 @@ mkdir -p gpurun_out
 ( timeout 600 ncu --set full --clock-control none -k regex:ntt_pass --launch-skip 3 -c 3 -o gpurun_out/r02_ntt_full -f python tools/ntt_probe.py 24 > gpurun_out/r02_ncu_ntt.log 2>&1 )
 ncu -i gpurun_out/r02_ntt_full.ncu-rep --page raw --csv > gpurun_out/r02_ntt_full_raw.csv 2>/dev/null
 rm -f gpurun_out/r02_ntt_full.ncu-rep
+( timeout 400 ncu --metrics gpu__time_duration.sum --clock-control none -c 4000 --csv --log-file gpurun_out/r02_launches.csv python bench.py --steps 1 --warmup 1 --no-extras --no-cpu --no-verify > gpurun_out/r02_ncu_bench.log 2>&1 )
 cat gpurun_out/r02_pytest_gpu_final.txt gpurun_out/r02_smoke_final.txt; tail -3 gpurun_out/r02_ncu_ntt.log
 python - <<'PY'
 import json
