@@ -53,6 +53,16 @@ extern "C" {
     pub fn b2s_pk_serialized_size(ctx: *const B2sCtx, pk: *const B2sPk, vk_len: u64, compressed: i32) -> u64;
     pub fn b2s_pk_serialize(ctx: *mut B2sCtx, pk: *const B2sPk, vk_bytes: *const u8, vk_len: u64, compressed: i32,
                             out: *mut u8, cap: u64) -> i32;
+    // universal-setup schemes (UniversalSetupSNARK, snark/src/lib.rs:107-133): the seams a polynomial-commitment /
+    // evaluation-domain backend binds.  mem: 0 host, 1 device; s, c, z: one Montgomery Fr on the host
+    pub fn b2s_ntt(ctx: *mut B2sCtx, data: *mut c_void, log_n: u32, inverse: i32, coset: i32, mem: i32) -> i32;
+    pub fn b2s_msm_g1(ctx: *mut B2sCtx, bases: *const c_void, scalars: *const c_void, n: u64, scalars_mont: i32, mem: i32,
+                      out_affine: *mut c_void) -> i32;
+    pub fn b2s_fixed_base_g1(ctx: *mut B2sCtx, scalars: *const c_void, n: u64, scalars_mont: i32, mem: i32, out: *mut c_void) -> i32;
+    pub fn b2s_poly_op(ctx: *mut B2sCtx, op: i32, a: *const c_void, b: *const c_void, s: *const c_void, out: *mut c_void,
+                       n: u64, mem: i32) -> i32;
+    pub fn b2s_poly_geom(ctx: *mut B2sCtx, c: *const c_void, s: *const c_void, n: u64, mem: i32, out: *mut c_void) -> i32;
+    pub fn b2s_poly_eval(ctx: *mut B2sCtx, coeffs: *const c_void, n: u64, z: *const c_void, mem: i32, out: *mut c_void) -> i32;
 }
 #[repr(C)]
 pub struct B2sGroup {
