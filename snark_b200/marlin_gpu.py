@@ -7,8 +7,6 @@ used for what the task allows it for: device memory, copies and views.  All torc
 only commitments, evaluations and challenges come back to the host.
 
 There is no CPU substitute: without libb200snark.so or without an sm_100 GPU the constructor raises."""
-import ctypes
-
 import numpy as np
 
 from . import lib as L

@@ -14,7 +14,7 @@ from snark_b200 import marlin as M
 def circuits(curve):
     out = []
     for cs in (orc.circuit2(curve, 1, 1, 2), orc.dummy_circuit(curve, 3, 5, 8, 8), orc.bench_circuit(curve, 9, seed=2),
-               orc.circuit1(curve, 3, 5) if False else orc.dummy_circuit(curve, 2, 7, 20, 13)):
+               orc.dummy_circuit(curve, 2, 7, 20, 13)):
         cs.finalize()
         assert cs.is_satisfied()
         out.append((cs.to_matrices(), list(cs.instance_assignment), list(cs.witness_assignment)))
