@@ -5,7 +5,8 @@ BASELINE.json's metric is quoted on, through libb200snark.so on 1..8 B200s; plus
   python bench.py --gpus N --steps K --warmup W            (torchrun for N > 1, one rank per GPU)
   python bench.py --impl reference ...                     (CPU restatement of the reference algorithms)
 
-One "step" = one proof: R1CS matrices x witness (SpMV) -> 7 NTTs -> 4 G1 MSMs + 1 G2 MSM -> epilogue.
+One "step" = one proof: R1CS matrices x witness (SpMV) -> witness_map (the reference algorithm's 7 NTTs; 6 are executed, r1cs.cu) ->
+4 G1 MSMs + 1 G2 MSM -> epilogue.  Algorithmic bytes stay SURVEY 8(d)'s figure for the reference algorithm (7 transforms).
 `value` times proofs with z already resident in HBM; `e2e` times the public C-ABI call with z in pinned
 host memory (H2D inside) and the proof read back to the host.  N > 1: strong scaling -- the five MSMs
 are cut by base range over the ranks (each rank holds 1/N of the proving key), partial sums are

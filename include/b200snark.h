@@ -134,7 +134,9 @@ int32_t b2s_r1cs_upload_lcmap(b2s_ctx* ctx, uint64_t n_rows, uint64_t n_instance
 void b2s_r1cs_free(b2s_ctx* ctx, b2s_r1cs* m);
 /* out_k[i] = <M_k row i, z>, i < n_rows; z has n_instance + n_witness elements.  All buffers share `mem`. */
 int32_t b2s_spmv(b2s_ctx* ctx, const b2s_r1cs* m, const void* z, int32_t mem, void* out_a, void* out_b, void* out_c);
-/* h = LibsnarkReduction::witness_map: SpMV -> 3 iNTT -> 3 coset NTT -> (ab-c)/Z -> coset iNTT.
+/* h = LibsnarkReduction::witness_map (SpMV -> 3 iNTT -> 3 coset NTT -> (ab-c)/Z -> coset iNTT), computed with
+ * six transforms: Z is constant on the coset and deg C < N, so h = (cosetiNTT(a_coset b_coset) - iNTT(c)) / Z(g) -- the same
+ * field elements for every assignment.
  * out_h receives domain_size elements (the top one is 0); domain_size = next_pow2(n_rows + n_instance). */
 int32_t b2s_witness_map(b2s_ctx* ctx, const b2s_r1cs* m, const void* z, int32_t mem, void* out_h);
 uint64_t b2s_r1cs_domain_size(const b2s_r1cs* m);

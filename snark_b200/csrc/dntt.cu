@@ -1,4 +1,4 @@
-// Distributed witness_map: the seven transforms of the LibsnarkReduction cut over G = 2^lg ranks by the
+// Distributed witness_map: the transforms of the LibsnarkReduction (six of them, see r1cs.cu) cut over G = 2^lg ranks by the
 // four-step (Bailey) schedule, SpMV and the pointwise quotient on the same distribution.
 //
 // Distribution.  N = 2^n (n even), N1 = N2 = 2^(n/2).  A vector x[i], i = i1 N2 + i2, is held by the rank that owns the

@@ -214,7 +214,7 @@ static int32_t shard_t(Ctx* c, const b2s_pk* pk, const b2s_r1cs* m, const void* 
     P1* g1 = reinterpret_cast<P1*>(g1_out);
     P1* w1 = tails.as<P1>();
     void* w2 = w1 + 4 * 64;
-    // Fork: the witness map (SpMV, seven transforms, quotient -- or its distributed form) is enqueued on the side stream and
+    // Fork: the witness map (SpMV, six transforms, quotient -- or its distributed form) is enqueued on the side stream and
     // runs side by side with the four MSMs that only need z; the h-query MSM joins them.  The ctx's launch stream is swapped
     // for the duration of the enqueue (everything below the C ABI launches and allocates on c->stream).
     const void* h_shard = nullptr;
