@@ -138,6 +138,14 @@ def transpose_rows(rows, n_out_rows):
     return out
 
 
+def universal_setup(be, compute_bound: int, tau: int):
+    """`UniversalSetupSNARK::universal_setup(compute_bound, rng)` (snark/src/lib.rs:117-123): public parameters good for every
+    circuit whose `index_shape(...).D` is at most `compute_bound` -- the KZG10 powers tau^i G1, i <= compute_bound, resident
+    in the backend.  The trait draws tau from `rng`; here the caller passes it (tests and the bench need the trapdoor for the
+    pairing-free opening check; a production caller draws it and forgets it)."""
+    return be.setup(compute_bound + 1, tau)
+
+
 def index(be, srs, mats, n_inst: int, n_vars: int):
     """`UniversalSetupSNARK::index` (snark/src/lib.rs:125-132): circuit-specific keys from the universal SRS.
     mats: A, B, C as row lists [(coeff, column)], the form `to_matrices()` exports

@@ -65,8 +65,10 @@ def test_unsatisfied_witness_is_rejected():
     be = om.IntBackend(curve)
     mats, x, w = circuits(curve)[1]
     info = M.index_shape(mats, len(x), len(x) + len(w))
-    srs = be.setup(info.D + 1, 0x1234567)
+    srs = M.universal_setup(be, info.D, 0x1234567)
     pk, vk = M.index(be, srs, mats, len(x), len(x) + len(w))
+    with pytest.raises(AssertionError):
+        M.index(be, M.universal_setup(be, info.D - 1, 0x1234567), mats, len(x), len(x) + len(w))     # compute bound too small
     w_bad = list(w)
     w_bad[0] = (w_bad[0] + 1) % curve.r
     with pytest.raises(AssertionError):
