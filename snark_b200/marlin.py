@@ -359,3 +359,61 @@ def kzg_open_batch(be, srs, polys, vals, z: int, xi: int, size: int):
     q_e = be.mul(be.add_scalar(e, r - v), be.inv0(be.add_scalar(pts, r - z)))
     q_c = be.ntt(q_e, inverse=True, coset=True)
     return be.commit(srs, be.slice(q_c, 0, size - 1))              # deg q <= deg p - 1 <= size - 2; the rest of q_c is zero
+
+
+# ---- wire form (the trait bounds Proof / VerifyingKey by CanonicalSerialize + CanonicalDeserialize, snark/src/lib.rs:25-36) -------
+# The repository's own framing, not ark-marlin's (nothing to pin that to): u32 little-endian counts, G1 points as uncompressed
+# affine (x, y) canonical little-endian with all-zero bytes for the point at infinity, field elements canonical little-endian.
+def _put_points(pts, fq_bytes):
+    out = [len(pts).to_bytes(4, "little")]
+    for P in pts:
+        out.append(bytes(2 * fq_bytes) if P is None else int(P[0]).to_bytes(fq_bytes, "little") + int(P[1]).to_bytes(fq_bytes, "little"))
+    return b"".join(out)
+
+
+def _get_points(buf, off, fq_bytes):
+    n = int.from_bytes(buf[off:off + 4], "little")
+    off += 4
+    pts = []
+    for _ in range(n):
+        x = int.from_bytes(buf[off:off + fq_bytes], "little")
+        y = int.from_bytes(buf[off + fq_bytes:off + 2 * fq_bytes], "little")
+        pts.append(None if x == 0 and y == 0 else (x, y))
+        off += 2 * fq_bytes
+    return pts, off
+
+
+def proof_to_bytes(proof: Proof, r: int, fq_bytes: int) -> bytes:
+    fr_bytes = (r.bit_length() + 7) // 8
+    ints = list(proof.evals1) + list(proof.evals2)
+    return (_put_points(proof.comms, fq_bytes) + _put_points(proof.openings, fq_bytes) + len(proof.evals1).to_bytes(4, "little") +
+            len(proof.evals2).to_bytes(4, "little") + b"".join(int(v).to_bytes(fr_bytes, "little") for v in ints))
+
+
+def proof_from_bytes(buf: bytes, r: int, fq_bytes: int) -> Proof:
+    fr_bytes = (r.bit_length() + 7) // 8
+    comms, off = _get_points(buf, 0, fq_bytes)
+    openings, off = _get_points(buf, off, fq_bytes)
+    n1 = int.from_bytes(buf[off:off + 4], "little")
+    n2 = int.from_bytes(buf[off + 4:off + 8], "little")
+    off += 8
+    if len(buf) != off + (n1 + n2) * fr_bytes:
+        raise ValueError("proof bytes: length does not match the declared counts")
+    vals = [int.from_bytes(buf[off + i * fr_bytes:off + (i + 1) * fr_bytes], "little") for i in range(n1 + n2)]
+    if any(v >= r for v in vals):
+        raise ValueError("proof bytes: non-canonical field element")
+    return Proof(comms, vals[:n1], vals[n1:], openings)
+
+
+def vk_to_bytes(vk: VerifierKey, fq_bytes: int) -> bytes:
+    i = vk.info
+    head = b"".join(int(v).to_bytes(8, "little") for v in (i.n_rows, i.n_inst, i.n_vars, i.n, i.m, i.l, i.D))
+    return head + _put_points(vk.index_comms, fq_bytes)
+
+
+def vk_from_bytes(buf: bytes, fq_bytes: int) -> VerifierKey:
+    f = [int.from_bytes(buf[8 * k:8 * k + 8], "little") for k in range(7)]
+    comms, off = _get_points(buf, 56, fq_bytes)
+    if off != len(buf):
+        raise ValueError("verifier key bytes: trailing data")
+    return VerifierKey(IndexInfo(*f), comms)

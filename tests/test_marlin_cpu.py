@@ -112,3 +112,26 @@ def test_real_pairing_opening_check():
     bad = copy.deepcopy(proof)
     bad.evals2[3] = (bad.evals2[3] + 1) % curve.r
     assert not om.verify(curve, vk, x, bad, tau_g2=tau_g2, engine=eng)
+
+
+def test_wire_form_round_trip():
+    curve = BN254
+    be = om.IntBackend(curve)
+    mats, x, w = circuits(curve)[2]
+    info = M.index_shape(mats, len(x), len(x) + len(w))
+    tau = 0x77777
+    pk, vk = M.index(be, M.universal_setup(be, info.D, tau), mats, len(x), len(x) + len(w))
+    proof = M.prove(be, pk, x, w)
+    raw = M.proof_to_bytes(proof, curve.r, be.fq_bytes)
+    assert len(raw) == 4 + 10 * 64 + 4 + 2 * 64 + 8 + 20 * 32
+    back = M.proof_from_bytes(raw, curve.r, be.fq_bytes)
+    assert (back.comms, back.evals1, back.evals2, back.openings) == (proof.comms, proof.evals1, proof.evals2, proof.openings)
+    vk2 = M.vk_from_bytes(M.vk_to_bytes(vk, be.fq_bytes), be.fq_bytes)
+    assert vk2.info == vk.info and vk2.index_comms == vk.index_comms
+    assert om.verify(curve, vk2, x, back, tau=tau)
+    with pytest.raises(ValueError):
+        M.proof_from_bytes(raw[:-1], curve.r, be.fq_bytes)
+    bad = bytearray(raw)
+    bad[-32:] = (curve.r).to_bytes(32, "little")                      # a non-canonical evaluation
+    with pytest.raises(ValueError):
+        M.proof_from_bytes(bytes(bad), curve.r, be.fq_bytes)
